@@ -1,0 +1,172 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes loader for the parity oracle.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import
+this package.  The product package ``plssvm_b200`` never does (tests/test_boundary.py checks that).
+
+Two builds expose the same C ABI (oracle/oracle_capi.cpp):
+
+* ``port``      — ``oracle/liboracle_port.so``: the reference's algorithm restated in ``oracle/lssvm_oracle.hpp``
+* ``reference`` — ``oracle/_ref/liboracle_ref.so``: the reference's own OpenMP kernel translation units
+  (``src/plssvm/backends/OpenMP/{svm_kernel,q_kernel}.cpp``) compiled in place from ``/root/reference`` and driven by
+  the restated CG / predict loops (``OpenMP/csvm.cpp:71-183,188-227,255-280`` cannot be compiled offline: igor, fast_float).
+
+Parity status: PINNED — tests/test_oracle_golden.py checks both builds against the reference's known-answer tests
+(``tests/backends/generic_csvm_tests.hpp:99-137,149-195,197-247``) and the ``port`` build against the ``reference`` build.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LINEAR, POLYNOMIAL, RBF = 0, 1, 2
+KERNEL_IDS = {"linear": LINEAR, "polynomial": POLYNOMIAL, "rbf": RBF}
+
+_PATHS = {
+    "port": os.path.join(_HERE, "liboracle_port.so"),
+    "reference": os.path.join(_HERE, "_ref", "liboracle_ref.so"),
+    "port_fast": os.path.join(_HERE, "liboracle_port_fast.so"),
+    "reference_fast": os.path.join(_HERE, "_ref", "liboracle_ref_fast.so"),
+}
+
+
+def build(targets=("port", "ref")) -> None:
+    """Compile the oracle (``make -C oracle port ref``).  ``ref`` is a no-op where /root/reference does not exist."""
+    subprocess.run(["make", "-s", "-C", _HERE, *targets], check=True)
+
+
+def available(kind: str) -> bool:
+    return os.path.exists(_PATHS[kind])
+
+
+class Oracle:
+    """One loaded oracle build.  All arrays are C-contiguous numpy arrays of the build's dtype (float32 or float64)."""
+
+    def __init__(self, kind: str = "port"):
+        if kind not in _PATHS:
+            raise ValueError(f"unknown oracle kind {kind!r}")
+        if not available(kind) and kind == "port":
+            build(("port",))
+        if not available(kind):
+            raise FileNotFoundError(f"oracle build {kind!r} not found at {_PATHS[kind]} (run `make -C oracle`)")
+        self.kind = kind
+        self.lib = ctypes.CDLL(_PATHS[kind])
+        self.lib.oracle_kind.restype = ctypes.c_char_p
+        self.lib.oracle_max_threads.restype = ctypes.c_int
+        for suf, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            p = ctypes.c_void_p
+            sz = ctypes.c_size_t
+            i = ctypes.c_int
+            getattr(self.lib, f"oracle_kernel_function_{suf}").restype = ct
+            getattr(self.lib, f"oracle_kernel_function_{suf}").argtypes = [i, p, p, sz, i, ct, ct]
+            getattr(self.lib, f"oracle_q_{suf}").restype = None
+            getattr(self.lib, f"oracle_q_{suf}").argtypes = [i, p, sz, sz, i, ct, ct, p]
+            getattr(self.lib, f"oracle_matvec_{suf}").restype = None
+            getattr(self.lib, f"oracle_matvec_{suf}").argtypes = [i, p, sz, sz, p, p, p, ct, ct, ct, i, ct, ct]
+            getattr(self.lib, f"oracle_solve_{suf}").restype = i
+            getattr(self.lib, f"oracle_solve_{suf}").argtypes = [i, p, sz, sz, p, i, ct, ct, ct, ct, ctypes.c_uint64, p, p, p, p, p]
+            getattr(self.lib, f"oracle_w_{suf}").restype = None
+            getattr(self.lib, f"oracle_w_{suf}").argtypes = [p, sz, sz, p, p]
+            getattr(self.lib, f"oracle_predict_{suf}").restype = None
+            getattr(self.lib, f"oracle_predict_{suf}").argtypes = [i, p, sz, sz, p, ct, p, p, p, sz, i, ct, ct, p]
+
+    # -- helpers ------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _suf(a: np.ndarray) -> str:
+        if a.dtype == np.float64:
+            return "f64"
+        if a.dtype == np.float32:
+            return "f32"
+        raise TypeError(f"unsupported dtype {a.dtype}")
+
+    @staticmethod
+    def _c(a: np.ndarray, dtype=None) -> np.ndarray:
+        return np.ascontiguousarray(a, dtype=dtype if dtype is not None else a.dtype)
+
+    @staticmethod
+    def _ptr(a: Optional[np.ndarray]):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def reported_kind(self) -> str:
+        return self.lib.oracle_kind().decode()
+
+    def set_threads(self, n: int) -> None:
+        self.lib.oracle_set_threads(int(n))
+
+    def max_threads(self) -> int:
+        return int(self.lib.oracle_max_threads())
+
+    # -- the path ------------------------------------------------------------------------------------------------------
+    def kernel_function(self, kernel: int, x, y, degree=3, gamma=1.0, coef0=0.0):
+        x = self._c(x)
+        y = self._c(y, x.dtype)
+        return getattr(self.lib, f"oracle_kernel_function_{self._suf(x)}")(kernel, self._ptr(x), self._ptr(y), x.size, degree, gamma, coef0)
+
+    def q(self, kernel: int, X, degree=3, gamma=1.0, coef0=0.0) -> np.ndarray:
+        X = self._c(X)
+        N, d = X.shape
+        q = np.empty(N - 1, dtype=X.dtype)
+        getattr(self.lib, f"oracle_q_{self._suf(X)}")(kernel, self._ptr(X), N, d, degree, gamma, coef0, self._ptr(q))
+        return q
+
+    def matvec(self, kernel: int, X, q, v, ret, QA_cost, cost_inv, add, degree=3, gamma=1.0, coef0=0.0) -> np.ndarray:
+        """ret += add * Q~ v  (``cost_inv`` = 1 / C, as the reference kernels take it).  Returns the updated copy of ``ret``."""
+        X = self._c(X)
+        N, d = X.shape
+        q = self._c(q, X.dtype)
+        v = self._c(v, X.dtype)
+        out = np.array(ret, dtype=X.dtype, copy=True)
+        getattr(self.lib, f"oracle_matvec_{self._suf(X)}")(kernel, self._ptr(X), N, d, self._ptr(q), self._ptr(v), self._ptr(out), QA_cost, cost_inv, add, degree, gamma, coef0)
+        return out
+
+    def solve(self, kernel: int, X, y, degree=3, gamma=1.0, coef0=0.0, cost=1.0, eps=1e-3, max_iter=None, trace=False):
+        X = self._c(X)
+        N, d = X.shape
+        y = self._c(y, X.dtype)
+        max_iter = int(N if max_iter is None else max_iter)
+        alpha = np.empty(N, dtype=X.dtype)
+        rho = np.zeros(1, dtype=X.dtype)
+        iters = np.zeros(1, dtype=np.uint64)
+        delta = np.zeros(2, dtype=X.dtype)
+        tr = np.full(max_iter + 1, np.nan, dtype=X.dtype) if trace else None
+        rc = getattr(self.lib, f"oracle_solve_{self._suf(X)}")(kernel, self._ptr(X), N, d, self._ptr(y), degree, gamma, coef0, cost, eps, max_iter,
+                                                               self._ptr(alpha), self._ptr(rho), self._ptr(iters), self._ptr(delta), self._ptr(tr))
+        if rc != 0:
+            raise ValueError("oracle_solve: invalid arguments")
+        res = {"alpha": alpha, "rho": rho[0], "iterations": int(iters[0]), "delta": delta[0], "delta0": delta[1]}
+        if trace:
+            res["trace"] = tr[: int(iters[0]) + 1]
+        return res
+
+    def w(self, SV, alpha) -> np.ndarray:
+        SV = self._c(SV)
+        n_sv, d = SV.shape
+        alpha = self._c(alpha, SV.dtype)
+        w = np.empty(d, dtype=SV.dtype)
+        getattr(self.lib, f"oracle_w_{self._suf(SV)}")(self._ptr(SV), n_sv, d, self._ptr(alpha), self._ptr(w))
+        return w
+
+    def predict(self, kernel: int, SV, alpha, rho, P, degree=3, gamma=1.0, coef0=0.0, w=None):
+        """Returns (decision values, w) — ``w`` is filled iff the kernel is linear (csvm.cpp:204-207)."""
+        SV = self._c(SV)
+        n_sv, d = SV.shape
+        P = self._c(P, SV.dtype)
+        alpha = self._c(alpha, SV.dtype)
+        out = np.empty(P.shape[0], dtype=SV.dtype)
+        w_buf = np.zeros(d, dtype=SV.dtype)
+        w_valid = ctypes.c_int(0)
+        if w is not None and len(w) > 0:
+            w_buf[:] = w
+            w_valid.value = 1
+        getattr(self.lib, f"oracle_predict_{self._suf(SV)}")(kernel, self._ptr(SV), n_sv, d, self._ptr(alpha), rho, self._ptr(w_buf), ctypes.byref(w_valid),
+                                                             self._ptr(P), P.shape[0], degree, gamma, coef0, self._ptr(out))
+        return out, (w_buf if w_valid.value else None)
+
+
+def sign_labels(values: np.ndarray) -> np.ndarray:
+    """csvm.hpp:337-340 + operators.hpp:178-181: label = value > 0 ? +1 : -1 (0 maps to -1)."""
+    return np.where(values > 0, 1, -1).astype(np.int32)
