@@ -128,6 +128,21 @@ def main():
         out[f"{name}/matvec_p"] = ref.matvec(kid, X, q, c["v"], np.zeros(X.shape[0] - 1, X.dtype), qa, 1.0 / c["cost"], 1.0, **pr)
         out[f"{name}/matvec_m"] = ref.matvec(kid, X, q, c["v"], c["v"], qa, 1.0 / c["cost"], -1.0, **pr)
         res = ref.solve(kid, X, y, cost=c["cost"], eps=c["eps"], max_iter=c["max_iter"], trace=True, **pr)
+        # The reference is not run-to-run reproducible (atomics: SURVEY.md §5) and CG amplifies the rounding noise, so the
+        # fixture also records the reference's OWN spread over repeated runs with 8/1/3/5 threads: parity tolerances for
+        # alpha/rho are max(stated tolerance, 20 x this spread).
+        spread_a, spread_r, iters = 0.0, 0.0, {res["iterations"]}
+        for nthr in (8, 1, 3, 5, 8):
+            ref.set_threads(nthr)
+            again = ref.solve(kid, X, y, cost=c["cost"], eps=c["eps"], max_iter=c["max_iter"], **pr)
+            iters.add(again["iterations"])
+            if again["iterations"] == res["iterations"]:
+                spread_a = max(spread_a, float(np.max(np.abs(again["alpha"] - res["alpha"])) / np.max(np.abs(res["alpha"]))))
+                spread_r = max(spread_r, float(abs(again["rho"] - res["rho"])))
+        ref.set_threads(8)
+        out[f"{name}/alpha_spread"] = np.asarray(spread_a)
+        out[f"{name}/rho_spread"] = np.asarray(spread_r)
+        out[f"{name}/iterations_seen"] = np.asarray(sorted(iters))
         out[f"{name}/alpha"] = res["alpha"]
         out[f"{name}/rho"] = np.asarray(res["rho"])
         out[f"{name}/iterations"] = np.asarray(res["iterations"])
@@ -136,6 +151,7 @@ def main():
         out[f"{name}/predict"] = vals
         if w is not None:
             out[f"{name}/w"] = w
+        print(f"{name}: spread alpha {spread_a:.1e} rho {spread_r:.1e} iters {sorted(iters)}")
         print(f"{name}: {res['iterations']} iterations, delta {res['delta']:.3e} / delta0 {res['delta0']:.3e}, min|f| {np.abs(vals).min():.2e}")
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)
 
