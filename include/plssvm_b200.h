@@ -1,0 +1,142 @@
+/*
+ * plssvm_b200 — C ABI of the Blackwell-native LS-SVM compute backend (libplssvm_b200.so).
+ *
+ * This is the drop-in boundary for the reference's `detail::gpu_csvm` hot path (PLSSVM v2.0.0).  The reference has no
+ * FFI: a backend is a C++ class overriding four protected virtuals of `plssvm::csvm` (include/plssvm/csvm.hpp:188-208).
+ * Each entry point below names the reference interface it replaces; the C++ adaptor that turns these calls back into a
+ * `plssvm::csvm` subclass is include/plssvm_b200/csvm.hpp, and INTEGRATION.md shows the reference-side registration.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; matrices are dense ROW-MAJOR (one data point per row, `d` contiguous features) —
+ *     exactly the rows of the reference's `std::vector<std::vector<real_type>>`
+ *   - `_f32` / `_f64` = the reference's `real_type` (float / double); all arithmetic runs in that type
+ *   - kernel ids follow `plssvm::kernel_function_type` (include/plssvm/kernel_function_types.hpp:31-38)
+ *   - every function returns 0 on success; otherwise `plssvm_b200_last_error()` holds the message the C++ adaptor
+ *     rethrows as `plssvm::b200::backend_exception` (reference: CUDA/detail/utility.cu:17-21)
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with PLSSVM_B200_ERR_CUDA
+ *   - not re-entrant per context (the reference's csvm is single-threaded by contract)
+ */
+#ifndef PLSSVM_B200_H_
+#define PLSSVM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* the library is built with -fvisibility=hidden: only the entry points below are exported */
+#pragma GCC visibility push(default)
+
+#define PLSSVM_B200_KERNEL_LINEAR 0
+#define PLSSVM_B200_KERNEL_POLYNOMIAL 1
+#define PLSSVM_B200_KERNEL_RBF 2
+
+#define PLSSVM_B200_OK 0
+#define PLSSVM_B200_ERR_INVALID 1 /* bad argument (the reference asserts: gpu_csvm.hpp:484-489, 664-672) */
+#define PLSSVM_B200_ERR_CUDA 2    /* CUDA / NCCL runtime failure, or no device */
+#define PLSSVM_B200_ERR_INTERNAL 3
+
+typedef struct plssvm_b200_ctx plssvm_b200_ctx;         /* one per GPU / rank; replaces cuda::csvm::init (CUDA/csvm.cu:48-86) */
+typedef struct plssvm_b200_dataset plssvm_b200_dataset; /* a dense matrix resident in HBM; replaces setup_data_on_device (gpu_csvm.hpp:302-346) */
+
+/* device-side timings of the last solve / predict on a context (CUDA events on the compute stream) */
+typedef struct plssvm_b200_timings {
+    double total_ms;          /* whole call (upload + q + CG + download) measured on the host */
+    double cg_loop_ms;        /* the CG iteration loop only (device events), excluding setup and the initial residual */
+    double matvec_ms;         /* sum over all implicit matvec launches (tile kernel + partial reduction) */
+    double matvec_tile_ms;    /* sum over the tile kernels alone (the dominant kernel) */
+    uint64_t matvec_calls;    /* number of implicit matvecs (iterations + 1 + refreshes) */
+    uint64_t kernel_launches; /* number of kernels of this library launched by the call */
+    double matvec_flops;      /* algorithmic FLOPs of ONE matvec: d * n * (n + 1)   */
+    double h2d_bytes;
+    double d2h_bytes;
+    int impl_used;            /* 1 = SIMT FMA tiles, 2 = tensor-core tiles (fp64: TMA + DMMA) */
+    int reserved;
+} plssvm_b200_timings;
+
+/* ---- context ---------------------------------------------------------------------------------------------------- */
+int plssvm_b200_create(int device, plssvm_b200_ctx **out);
+int plssvm_b200_destroy(plssvm_b200_ctx *ctx);
+/* message of the last failed call on this thread (valid until the next call) */
+const char *plssvm_b200_last_error(void);
+/* tuning / debugging knobs: "impl" (0 auto, 1 simt, 2 tensor), "check_interval" (CG iterations between host polls),
+ * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571) */
+int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long value);
+int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out);
+int plssvm_b200_device_count(int *count);
+
+/* ---- multi-GPU: one context per rank, tiles of the triangle sharded by rank, NCCL all-reduce of the result vector.
+ * Replaces the reference's host-staged device_reduction (gpu_csvm.hpp:449-475).  `id` is NCCL's 128-byte unique id:
+ * rank 0 calls comm_unique_id, the launcher broadcasts it (torch.distributed / MPI / a file), every rank calls comm_init. */
+int plssvm_b200_comm_unique_id(void *id128);
+int plssvm_b200_comm_init(plssvm_b200_ctx *ctx, int rank, int world_size, const void *id128);
+
+/* host-only helpers (no CUDA needed): the banded tile schedule shared by kernels, ranks and tests */
+uint64_t plssvm_b200_tile_size(void);
+uint64_t plssvm_b200_tri_num_tiles(uint64_t tiles_per_side);
+uint64_t plssvm_b200_tri_encode(uint64_t tiles_per_side, uint64_t I, uint64_t J);
+void plssvm_b200_tri_decode(uint64_t tiles_per_side, uint64_t L, uint32_t *I, uint32_t *J);
+void plssvm_b200_rank_range(uint64_t total, int rank, int world_size, uint64_t *lo, uint64_t *hi);
+
+/* ---- datasets ----------------------------------------------------------------------------------------------------
+ * Upload (or adopt from device memory when src_on_device != 0) a dense row-major N x d matrix.  The library keeps its
+ * own padded copy (row pitch rounded up to 128 bytes, zero filled) plus the squared row norms. */
+int plssvm_b200_dataset_create_f32(plssvm_b200_ctx *ctx, const float *X, size_t N, size_t d, int src_on_device, plssvm_b200_dataset **out);
+int plssvm_b200_dataset_create_f64(plssvm_b200_ctx *ctx, const double *X, size_t N, size_t d, int src_on_device, plssvm_b200_dataset **out);
+int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds);
+
+/* ---- csvm::solve_system_of_linear_equations (csvm.hpp:188-192; gpu_csvm.hpp:477-654) ------------------------------
+ * Solves the reduced LS-SVM system with CG exactly as the reference does (x0 = 1, stop when r.r <= eps^2 r0.r0 or after
+ * max_iter iterations, residual refresh every 50th iteration).  X: N x d host matrix, y: N labels as +-1.
+ * Outputs: alpha[N] (last entry = -sum of the others), rho (= -bias), the iteration count min(iter + 1, max_iter), and
+ * residual[2] = { final r.r, initial r0.r0 } (either may be NULL). */
+int plssvm_b200_solve_f32(plssvm_b200_ctx *ctx, const float *X, size_t N, size_t d, const float *y, int kernel, int degree, float gamma, float coef0,
+                          float cost, float eps, uint64_t max_iter, float *alpha_out, float *rho_out, uint64_t *iters_out, float *residual_out);
+int plssvm_b200_solve_f64(plssvm_b200_ctx *ctx, const double *X, size_t N, size_t d, const double *y, int kernel, int degree, double gamma, double coef0,
+                          double cost, double eps, uint64_t max_iter, double *alpha_out, double *rho_out, uint64_t *iters_out, double *residual_out);
+/* same, on a matrix that is already resident in HBM (the timed region of the device-resident benchmark) */
+int plssvm_b200_solve_dataset_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const float *y, int kernel, int degree, float gamma, float coef0,
+                                  float cost, float eps, uint64_t max_iter, float *alpha_out, float *rho_out, uint64_t *iters_out, float *residual_out);
+int plssvm_b200_solve_dataset_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const double *y, int kernel, int degree, double gamma, double coef0,
+                                  double cost, double eps, uint64_t max_iter, double *alpha_out, double *rho_out, uint64_t *iters_out, double *residual_out);
+
+/* ---- csvm::predict_values (csvm.hpp:204-208; gpu_csvm.hpp:656-730) --------------------------------------------------
+ * out[p] = sum_i alpha_i k(sv_i, point_p) - rho.  Linear kernel: w = sum_i alpha_i sv_i is computed iff *w_valid == 0,
+ * stored in w_inout[d] and *w_valid set to 1 (the reference's `w` cache, gpu_csvm.hpp:696-698); other kernels leave
+ * w untouched.  Test points are streamed through HBM in batches, 64-bit indexing throughout. */
+int plssvm_b200_predict_f32(plssvm_b200_ctx *ctx, const float *SV, size_t n_sv, size_t d, const float *alpha, float rho, float *w_inout, int *w_valid,
+                            const float *points, size_t m, int kernel, int degree, float gamma, float coef0, float *out);
+int plssvm_b200_predict_f64(plssvm_b200_ctx *ctx, const double *SV, size_t n_sv, size_t d, const double *alpha, double rho, double *w_inout, int *w_valid,
+                            const double *points, size_t m, int kernel, int degree, double gamma, double coef0, double *out);
+int plssvm_b200_predict_dataset_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const float *alpha, float rho, float *w_inout, int *w_valid,
+                                    plssvm_b200_dataset *points, int kernel, int degree, float gamma, float coef0, float *out);
+int plssvm_b200_predict_dataset_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const double *alpha, double rho, double *w_inout, int *w_valid,
+                                    plssvm_b200_dataset *points, int kernel, int degree, double gamma, double coef0, double *out);
+
+/* ---- kernel-granular entry points = the reference's four run_*_kernel virtuals (gpu_csvm.hpp:208-277) -------------- */
+/* run_q_kernel (csvm.cu:110-129): q[i] = k(x_i, x_{N-1}) for i < N-1; *k_last = k(x_{N-1}, x_{N-1}) (QA_cost = *k_last + 1/C) */
+int plssvm_b200_q_kernel_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, int kernel, int degree, float gamma, float coef0, float *q_out, float *k_last);
+int plssvm_b200_q_kernel_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, int kernel, int degree, double gamma, double coef0, double *q_out, double *k_last);
+/* run_svm_kernel (csvm.cu:134-153): ret[0..N-2] += add * Q~ v with Q~_ij = k(x_i,x_j) + QA_cost - q_i - q_j + delta_ij * cost_inv,
+ * add in {+1, -1}, cost_inv = 1 / C — the argument convention of device_kernel_* (svm_kernel.cu:17) */
+int plssvm_b200_matvec_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const float *q, const float *v, float QA_cost, float cost_inv, float add,
+                           int kernel, int degree, float gamma, float coef0, float *ret_inout);
+int plssvm_b200_matvec_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const double *q, const double *v, double QA_cost, double cost_inv, double add,
+                           int kernel, int degree, double gamma, double coef0, double *ret_inout);
+/* run_w_kernel (csvm.cu:158-165): w[f] = sum_i alpha_i SV[i][f] over ALL n_sv rows */
+int plssvm_b200_w_kernel_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const float *alpha, float *w_out);
+int plssvm_b200_w_kernel_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const double *alpha, double *w_out);
+/* run_predict_kernel (csvm.cu:170-186): out[p] = sum_i alpha_i k(sv_i, point_p)  (no -rho; polynomial / rbf only) */
+int plssvm_b200_predict_kernel_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const float *alpha, plssvm_b200_dataset *points, int kernel, int degree,
+                                   float gamma, float coef0, float *out);
+int plssvm_b200_predict_kernel_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const double *alpha, plssvm_b200_dataset *points, int kernel, int degree,
+                                   double gamma, double coef0, double *out);
+
+#pragma GCC visibility pop
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSSVM_B200_H_ */

@@ -1,0 +1,927 @@
+// libplssvm_b200.so — host driver + C ABI (include/plssvm_b200.h).
+//
+// B200-native re-design of the reference's detail::gpu_csvm driver (include/plssvm/backends/gpu_csvm.hpp:45-730):
+//   * X lives once in HBM, row-major with a 128-byte-multiple pitch (TMA boxes + coalesced row streams), plus |x_i|^2
+//   * the CG loop is device-resident: all vectors AND scalars stay in HBM, the host only polls a convergence flag
+//     (the reference does 3 blocking PCIe copies + host-serial vector algebra per iteration, gpu_csvm.hpp:582-633)
+//   * the implicit matvec is a persistent tile kernel over the banded lower triangle (tile_dmma.cuh / tile_simt.cuh)
+//     followed by a fixed-order partial reduction — deterministic, no atomics
+//   * multi-GPU: each rank owns a contiguous share of the tile order, one ncclAllReduce of the n-vector per matvec
+//     (the reference: feature split for the linear kernel only, summed through the host, gpu_csvm.hpp:283-299,449-475)
+// There is no CPU fallback: without a device every compute entry point fails.
+#include "../../include/plssvm_b200.h"
+
+#include "common.cuh"
+#include "stream_kernels.cuh"
+#include "tile_dmma.cuh"
+#include "tile_simt.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error;
+
+struct api_error : std::runtime_error {
+    int code;
+    api_error(const int c, const std::string &msg) : std::runtime_error(msg), code(c) {}
+};
+
+#define PB_CUDA(call)                                                                                                                     \
+    do {                                                                                                                                  \
+        const cudaError_t err__ = (call);                                                                                                 \
+        if (err__ != cudaSuccess) {                                                                                                       \
+            throw api_error(PLSSVM_B200_ERR_CUDA, std::string("CUDA assert '") + cudaGetErrorName(err__) + "' (" + std::to_string(static_cast<int>(err__)) + "): " + \
+                                                      cudaGetErrorString(err__) + " [" #call "]");                                       \
+        }                                                                                                                                 \
+    } while (0)
+
+#define PB_REQUIRE(cond, msg)                                              \
+    do {                                                                   \
+        if (!(cond)) { throw api_error(PLSSVM_B200_ERR_INVALID, (msg)); }  \
+    } while (0)
+
+// ---- NCCL through dlopen (torch ships libnccl.so.2; nothing to link at build time) ---------------------------------------
+struct nccl_api {
+    using comm_t = void *;
+    struct unique_id {
+        char internal[128];
+    };
+    int (*GetUniqueId)(unique_id *) = nullptr;
+    int (*CommInitRank)(comm_t *, int, unique_id, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(comm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    void *handle = nullptr;
+
+    static nccl_api &get() {
+        static nccl_api api = load();
+        return api;
+    }
+    static nccl_api load() {
+        nccl_api a;
+        const char *names[] = { std::getenv("PLSSVM_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+        for (const char *nm : names) {
+            if (nm == nullptr) { continue; }
+            a.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (a.handle != nullptr) { break; }
+        }
+        if (a.handle == nullptr) { throw api_error(PLSSVM_B200_ERR_CUDA, "cannot load libnccl.so.2 (set PLSSVM_B200_NCCL_LIB)"); }
+        a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(a.handle, "ncclGetUniqueId"));
+        a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(a.handle, "ncclCommInitRank"));
+        a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(a.handle, "ncclAllReduce"));
+        a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.handle, "ncclCommDestroy"));
+        a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.handle, "ncclGetErrorString"));
+        if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString) {
+            throw api_error(PLSSVM_B200_ERR_CUDA, "libnccl is missing required symbols");
+        }
+        return a;
+    }
+    void check(const int rc, const char *what) const {
+        if (rc != 0) { throw api_error(PLSSVM_B200_ERR_CUDA, std::string("NCCL failure in ") + what + ": " + GetErrorString(rc)); }
+    }
+};
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+// ---- RAII device buffer (reference: gpu_device_ptr.hpp:28-239; here async on the context stream) -----------------------------
+template <typename T>
+struct dbuf {
+    T *p = nullptr;
+    std::size_t count = 0;
+    dbuf() = default;
+    explicit dbuf(const std::size_t n) { alloc(n); }
+    dbuf(const dbuf &) = delete;
+    dbuf &operator=(const dbuf &) = delete;
+    dbuf(dbuf &&o) noexcept : p(o.p), count(o.count) { o.p = nullptr; o.count = 0; }
+    dbuf &operator=(dbuf &&o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p;
+            count = o.count;
+            o.p = nullptr;
+            o.count = 0;
+        }
+        return *this;
+    }
+    ~dbuf() { release(); }
+    void alloc(const std::size_t n) {
+        release();
+        count = n;
+        if (n > 0) { PB_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T))); }
+    }
+    void release() {
+        if (p != nullptr) { cudaFree(p); }
+        p = nullptr;
+        count = 0;
+    }
+};
+
+struct event_pair_timer {
+    std::vector<cudaEvent_t> ev;
+    std::size_t used = 0;
+    static constexpr std::size_t MAX_PAIRS = 4096;
+    ~event_pair_timer() {
+        for (cudaEvent_t e : ev) { cudaEventDestroy(e); }
+    }
+    void reset() { used = 0; }
+    bool begin(cudaStream_t s) {
+        if (used / 2 >= MAX_PAIRS) { return false; }
+        if (ev.size() < used + 2) {
+            cudaEvent_t a, b;
+            PB_CUDA(cudaEventCreate(&a));
+            PB_CUDA(cudaEventCreate(&b));
+            ev.push_back(a);
+            ev.push_back(b);
+        }
+        PB_CUDA(cudaEventRecord(ev[used], s));
+        return true;
+    }
+    void end(cudaStream_t s) {
+        PB_CUDA(cudaEventRecord(ev[used + 1], s));
+        used += 2;
+    }
+    double total_ms() {
+        double t = 0.0;
+        for (std::size_t i = 0; i + 1 < used; i += 2) {
+            float ms = 0.f;
+            PB_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+            t += ms;
+        }
+        return t;
+    }
+};
+
+}  // namespace
+
+// ---- opaque handles ---------------------------------------------------------------------------------------------------------
+struct plssvm_b200_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    int rank = 0, world = 1;
+    nccl_api::comm_t comm = nullptr;
+    // options
+    int impl = 0;            // 0 auto, 1 simt, 2 tensor
+    int check_interval = 0;  // 0 = auto
+    int verbose = 0;
+    // timings of the last call
+    plssvm_b200_timings tm{};
+    event_pair_timer tile_timer, matvec_timer;
+    cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
+    PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
+    void *pinned = nullptr;  // small pinned staging block for scalar read-backs
+};
+
+struct plssvm_b200_dataset {
+    plssvm_b200_ctx *ctx = nullptr;
+    int elem_size = 0;  // 4 or 8
+    std::size_t N = 0, d = 0, ld = 0;
+    void *X = nullptr;   // [N][ld]
+    void *sq = nullptr;  // [N]
+};
+
+namespace {
+
+using pb::CGState;
+using pb::KernelParams;
+using pb::TileParams;
+using pb::TILE;
+
+template <typename T>
+std::size_t pitch_elems(const std::size_t d) {
+    const std::size_t per128 = 128 / sizeof(T);
+    return (d + per128 - 1) / per128 * per128;
+}
+
+void make_tensor_map_f64(plssvm_b200_ctx *ctx, CUtensorMap *tm, const double *base, const std::size_t rows, const std::size_t ld) {
+    const cuuint64_t dims[2] = { static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows) };
+    const cuuint64_t strides[1] = { static_cast<cuuint64_t>(ld * sizeof(double)) };
+    const cuuint32_t box[2] = { static_cast<cuuint32_t>(pb::DMMA_BK), static_cast<cuuint32_t>(TILE) };
+    const cuuint32_t estr[2] = { 1, 1 };
+    const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(rc))); }
+}
+
+template <typename T, int KERNEL, int MODE>
+void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
+    const std::uint64_t ntiles = p.tile_hi - p.tile_lo;
+    if (ntiles == 0) { return; }
+    const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
+    if constexpr (sizeof(T) == 8) {
+        if (impl == 2) {
+            CUtensorMap tmA, tmB;
+            make_tensor_map_f64(ctx, &tmA, p.A, p.n_rows, p.ld);
+            make_tensor_map_f64(ctx, &tmB, p.B, p.n_cols, p.ld);
+            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_dmma<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::DMMA_SMEM_BYTES));
+            pb::tile_kernel_dmma<KERNEL, MODE><<<grid, pb::DMMA_THREADS, pb::DMMA_SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+            return;
+        }
+    }
+    pb::tile_kernel_simt<T, KERNEL, MODE><<<grid, 256, 0, ctx->stream>>>(p);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+}
+
+template <typename T>
+int resolve_impl(const plssvm_b200_ctx *ctx) {
+    if (ctx->impl == 1) { return 1; }
+    return sizeof(T) == 8 ? 2 : 1;  // fp32 tensor path (tcgen05 3xTF32) not wired yet: SIMT
+}
+
+template <typename T, int MODE>
+void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p) {
+    const int impl = resolve_impl<T>(ctx);
+    ctx->tm.impl_used = impl;
+    switch (p.kp.kernel) {
+        case pb::K_LINEAR: launch_tiles_t<T, pb::K_LINEAR, MODE>(ctx, p, impl); break;
+        case pb::K_POLYNOMIAL: launch_tiles_t<T, pb::K_POLYNOMIAL, MODE>(ctx, p, impl); break;
+        default: launch_tiles_t<T, pb::K_RBF, MODE>(ctx, p, impl); break;
+    }
+}
+
+template <typename T>
+void all_reduce_sum(plssvm_b200_ctx *ctx, T *buf, const std::size_t count) {
+    if (ctx->world <= 1) { return; }
+    const nccl_api &nccl = nccl_api::get();
+    nccl.check(nccl.AllReduce(buf, buf, count, sizeof(T) == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32, NCCL_SUM, ctx->comm, ctx->stream), "ncclAllReduce");
+}
+
+void validate_kernel_args(const int kernel, const double gamma) {
+    PB_REQUIRE(kernel >= 0 && kernel <= 2, "unknown kernel function type " + std::to_string(kernel));
+    if (kernel != pb::K_LINEAR) { PB_REQUIRE(gamma > 0.0, "gamma must be greater than 0, but is " + std::to_string(gamma) + "!"); }
+}
+
+// ---- implicit matvec: out = Q~ v  (set semantics; callers add / subtract) ----------------------------------------------------
+template <typename T>
+struct matvec_plan {
+    plssvm_b200_ctx *ctx;
+    const plssvm_b200_dataset *ds;
+    std::uint32_t n;  // N - 1
+    std::uint32_t Tb; // tiles per side
+    std::uint64_t tile_lo, tile_hi;
+    dbuf<T> partial;
+    TileParams<T> base;
+
+    matvec_plan(plssvm_b200_ctx *c, const plssvm_b200_dataset *data, const KernelParams<T> &kp, const T *q, const T *QA_cost_dev, const T cost_inv, const int *done) :
+        ctx(c), ds(data) {
+        n = static_cast<std::uint32_t>(data->N - 1);
+        Tb = (n + TILE - 1) / TILE;
+        pb::rank_range(pb::tri_num_tiles(Tb), c->rank, c->world, tile_lo, tile_hi);
+        partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE);
+        base = TileParams<T>{};
+        base.A = static_cast<const T *>(data->X);
+        base.B = base.A;
+        base.n_rows = n;
+        base.n_cols = n;
+        base.ld = static_cast<std::uint32_t>(data->ld);
+        base.T_rows = Tb;
+        base.T_cols = Tb;
+        base.tile_lo = tile_lo;
+        base.tile_hi = tile_hi;
+        base.row_sq = static_cast<const T *>(data->sq);
+        base.col_sq = base.row_sq;
+        base.q = q;
+        base.QA_cost = QA_cost_dev;
+        base.cost_inv = cost_inv;
+        base.kp = kp;
+        base.partial = partial.p;
+        base.done = done;
+    }
+
+    // out = Q~ v
+    void run(const T *v, T *out) {
+        TileParams<T> p = base;
+        p.v = v;
+        const bool timed_mv = ctx->matvec_timer.begin(ctx->stream);
+        const bool timed = ctx->tile_timer.begin(ctx->stream);
+        launch_tiles<T, pb::MODE_SYM>(ctx, p);
+        if (timed) { ctx->tile_timer.end(ctx->stream); }
+        pb::reduce_partials_kernel<T, pb::MODE_SYM><<<Tb, 512, 0, ctx->stream>>>(partial.p, out, n, Tb, Tb, tile_lo, tile_hi, ctx->world > 1 ? 1 : 0, T(1), T(0), 0, base.done);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+        all_reduce_sum(ctx, out, n);
+        if (timed_mv) { ctx->matvec_timer.end(ctx->stream); }
+        ctx->tm.matvec_calls++;
+    }
+};
+
+template <typename T, typename F>
+void dispatch_kernel(const int kernel, F &&f) {
+    switch (kernel) {
+        case pb::K_LINEAR: f(std::integral_constant<int, pb::K_LINEAR>{}); break;
+        case pb::K_POLYNOMIAL: f(std::integral_constant<int, pb::K_POLYNOMIAL>{}); break;
+        default: f(std::integral_constant<int, pb::K_RBF>{}); break;
+    }
+}
+
+template <typename T>
+void run_q_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds, const KernelParams<T> &kp, T *q_full /* N */) {
+    const unsigned grid = static_cast<unsigned>((ds->N + 7) / 8);
+    dispatch_kernel<T>(kp.kernel, [&](auto K) {
+        pb::q_kernel<T, decltype(K)::value><<<grid, 256, 0, ctx->stream>>>(static_cast<const T *>(ds->X), ds->N, static_cast<std::uint32_t>(ds->ld), kp, q_full);
+    });
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+}
+
+void reset_timings(plssvm_b200_ctx *ctx) {
+    ctx->tm = plssvm_b200_timings{};
+    ctx->tile_timer.reset();
+    ctx->matvec_timer.reset();
+}
+
+void check_dataset(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds, const std::size_t elem, const char *what) {
+    PB_REQUIRE(ctx != nullptr, "context is NULL");
+    PB_REQUIRE(ds != nullptr, std::string(what) + " dataset is NULL");
+    PB_REQUIRE(ds->ctx == ctx, std::string(what) + " dataset belongs to another context");
+    PB_REQUIRE(ds->elem_size == static_cast<int>(elem), std::string(what) + " dataset has the wrong real_type");
+}
+
+// ---- dataset ----------------------------------------------------------------------------------------------------------------
+template <typename T>
+plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const T *X, const std::size_t N, const std::size_t d, const int src_on_device) {
+    PB_REQUIRE(ctx != nullptr, "context is NULL");
+    PB_REQUIRE(X != nullptr, "The data must not be empty!");
+    PB_REQUIRE(N > 0, "The data must not be empty!");
+    PB_REQUIRE(d > 0, "The data points must contain at least one feature!");
+    PB_REQUIRE(N < (1ull << 31) && d < (1ull << 31), "matrix dimensions must be below 2^31");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    auto *ds = new plssvm_b200_dataset{};
+    try {
+        ds->ctx = ctx;
+        ds->elem_size = static_cast<int>(sizeof(T));
+        ds->N = N;
+        ds->d = d;
+        ds->ld = pitch_elems<T>(d);
+        PB_CUDA(cudaMalloc(&ds->X, N * ds->ld * sizeof(T)));
+        PB_CUDA(cudaMalloc(&ds->sq, N * sizeof(T)));
+        if (src_on_device != 0) {
+            const std::size_t total = N * ds->ld;
+            const unsigned grid = static_cast<unsigned>(std::min<std::size_t>((total + 255) / 256, static_cast<std::size_t>(ctx->num_sms) * 32));
+            pb::pack_rows_kernel<T><<<grid, 256, 0, ctx->stream>>>(X, static_cast<T *>(ds->X), N, static_cast<std::uint32_t>(d), static_cast<std::uint32_t>(ds->ld));
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+        } else {
+            if (ds->ld != d) { PB_CUDA(cudaMemsetAsync(ds->X, 0, N * ds->ld * sizeof(T), ctx->stream)); }
+            PB_CUDA(cudaMemcpy2DAsync(ds->X, ds->ld * sizeof(T), X, d * sizeof(T), d * sizeof(T), N, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->tm.h2d_bytes += static_cast<double>(N * d * sizeof(T));
+        }
+        pb::row_norms_kernel<T><<<static_cast<unsigned>((N + 7) / 8), 256, 0, ctx->stream>>>(static_cast<const T *>(ds->X), N, static_cast<std::uint32_t>(ds->ld), static_cast<T *>(ds->sq));
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        cudaFree(ds->X);
+        cudaFree(ds->sq);
+        delete ds;
+        throw;
+    }
+    return ds;
+}
+
+// ---- solve: csvm::solve_system_of_linear_equations (gpu_csvm.hpp:477-654) ----------------------------------------------------
+template <typename T>
+void solve_dataset(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const T *y, const int kernel, const int degree, const T gamma, const T coef0, const T cost, const T eps,
+                   const std::uint64_t max_iter, T *alpha_out, T *rho_out, std::uint64_t *iters_out, T *residual_out) {
+    check_dataset(ctx, ds, sizeof(T), "training");
+    PB_REQUIRE(y != nullptr && alpha_out != nullptr && rho_out != nullptr, "y, alpha_out and rho_out must not be NULL");
+    PB_REQUIRE(ds->N >= 2, "The data must contain at least two data points!");
+    PB_REQUIRE(eps > T(0), "The stopping criterion in the CG algorithm must be greater than 0.0, but is " + std::to_string(eps) + "!");
+    PB_REQUIRE(max_iter > 0, "The number of CG iterations must be greater than 0!");
+    PB_REQUIRE(cost != T(0), "cost must not be 0.0!");
+    validate_kernel_args(kernel, static_cast<double>(gamma));
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    const std::size_t N = ds->N;
+    const std::uint32_t n = static_cast<std::uint32_t>(N - 1);
+    const KernelParams<T> kp{ kernel, degree, gamma, coef0 };
+    const unsigned vblocks = (n + pb::VEC_CHUNK - 1) / pb::VEC_CHUNK;
+
+    dbuf<T> y_d(N), q_full(N), b(n), x(n), r(n), dvec(n), Ad(n), part(vblocks);
+    dbuf<CGState<T>> state(1);
+    CGState<T> *h_state = static_cast<CGState<T> *>(ctx->pinned);
+    const int *done = &state.p->done;
+
+    PB_CUDA(cudaMemcpyAsync(y_d.p, y, N * sizeof(T), cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += static_cast<double>(N * sizeof(T));
+    PB_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CGState<T>), st));
+    pb::cg_init_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(y_d.p, n, b.p, x.p, state.p, cost);
+    run_q_kernel<T>(ctx, ds, kp, q_full.p);
+    pb::cg_qa_cost_kernel<T><<<1, 1, 0, st>>>(q_full.p, n, state.p, cost);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches += 2;
+
+    matvec_plan<T> mv(ctx, ds, kp, q_full.p, &state.p->QA_cost, T(1) / cost, done);
+    ctx->tm.matvec_flops = static_cast<double>(ds->d) * static_cast<double>(n) * (static_cast<double>(n) + 1.0);
+
+    // r = b - Q~ x0,  delta0 = r.r,  d = r     (gpu_csvm.hpp:515-554)
+    mv.run(x.p, Ad.p);
+    pb::cg_residual_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(b.p, Ad.p, r.p, n, part.p, nullptr);
+    pb::cg_start_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p);
+    pb::cg_update_d_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches += 3;
+
+    const auto enqueue_iteration = [&](const std::uint64_t iter) {
+        mv.run(dvec.p, Ad.p);                                                                                       // Ad = Q~ d        (574-582)
+        pb::dot_partial_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, Ad.p, n, part.p, done);
+        pb::cg_alpha_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p);                               // alpha = delta / d.Ad (585)
+        if (iter % 50 == 49) {                                                                                      // residual refresh (595-609)
+            pb::cg_update_xr_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(x.p, r.p, dvec.p, Ad.p, n, state.p, part.p);
+            mv.run(x.p, Ad.p);
+            pb::cg_residual_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(b.p, Ad.p, r.p, n, part.p, done);
+        } else {
+            pb::cg_update_xr_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(x.p, r.p, dvec.p, Ad.p, n, state.p, part.p);  // x += a d; r -= a Ad (588, 611-613)
+        }
+        pb::cg_beta_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p, eps, nullptr);                  // delta, stop test, beta (616-625)
+        pb::cg_update_d_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);                // d = beta d + r   (627)
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches += (iter % 50 == 49) ? 6 : 5;
+    };
+
+    // host only polls: every `interval` iterations one 100-byte read-back; kernels of iterations enqueued past convergence exit at once
+    std::uint64_t interval = ctx->check_interval > 0 ? static_cast<std::uint64_t>(ctx->check_interval) : (n >= 16384 ? 1 : 8);
+    PB_CUDA(cudaEventRecord(ctx->ev_loop0, st));
+    std::uint64_t it = 0;
+    while (it < max_iter) {
+        const std::uint64_t batch = std::min<std::uint64_t>(interval, max_iter - it);
+        for (std::uint64_t k = 0; k < batch; ++k) { enqueue_iteration(it + k); }
+        it += batch;
+        PB_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CGState<T>), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        if (ctx->verbose != 0) {
+            std::printf("[plssvm_b200] iteration %llu (max: %llu) residuum %g (target: %g)\n", static_cast<unsigned long long>(h_state->iter),
+                        static_cast<unsigned long long>(max_iter), static_cast<double>(h_state->delta), static_cast<double>(eps * eps * h_state->delta0));
+        }
+        if (h_state->done != 0) { break; }
+    }
+    PB_CUDA(cudaEventRecord(ctx->ev_loop1, st));
+
+    // bias and the last alpha (gpu_csvm.hpp:649-653)
+    pb::cg_finish_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(x.p, q_full.p, n, state.p);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+    PB_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CGState<T>), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaMemcpyAsync(alpha_out, x.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    ctx->tm.d2h_bytes += static_cast<double>(n * sizeof(T));
+    alpha_out[n] = -h_state->sum_x;
+    *rho_out = -h_state->bias;
+    if (iters_out != nullptr) { *iters_out = std::min<std::uint64_t>(h_state->iter, max_iter); }
+    if (residual_out != nullptr) {
+        residual_out[0] = h_state->delta;
+        residual_out[1] = h_state->delta0;
+    }
+    if (ctx->verbose != 0) {
+        std::printf("[plssvm_b200] optimization finished, #iter = %llu\n", static_cast<unsigned long long>(std::min<std::uint64_t>(h_state->iter, max_iter)));
+    }
+    float loop_ms = 0.f;
+    PB_CUDA(cudaEventElapsedTime(&loop_ms, ctx->ev_loop0, ctx->ev_loop1));
+    ctx->tm.cg_loop_ms = loop_ms;
+    ctx->tm.matvec_tile_ms = ctx->tile_timer.total_ms();
+    ctx->tm.matvec_ms = ctx->matvec_timer.total_ms();
+}
+
+// ---- w-kernel -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+void run_w_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, T *w_d /* ld entries, zero padded */) {
+    const std::uint32_t d = static_cast<std::uint32_t>(sv->d);
+    const std::uint32_t chunks = static_cast<std::uint32_t>((sv->N + pb::W_ROWS - 1) / pb::W_ROWS);
+    dbuf<T> part(static_cast<std::size_t>(chunks) * d);
+    PB_CUDA(cudaMemsetAsync(w_d, 0, sv->ld * sizeof(T), ctx->stream));
+    const dim3 grid((d + 255) / 256, chunks);
+    pb::w_partial_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T *>(sv->X), alpha_d, sv->N, d, static_cast<std::uint32_t>(sv->ld), part.p);
+    pb::w_reduce_kernel<T><<<(d + 255) / 256, 256, 0, ctx->stream>>>(part.p, chunks, d, w_d);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches += 2;
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));  // `part` is freed on return
+}
+
+// ---- predict: csvm::predict_values (gpu_csvm.hpp:656-730) -------------------------------------------------------------------------
+// points: `pts` rows [p0, p0 + m) of a resident matrix; out_d: m values on the device
+template <typename T>
+void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, const T *w_d, const T rho, const T *P, const T *P_sq, const std::size_t m,
+                         const KernelParams<T> &kp, T *out_d, dbuf<T> &partial) {
+    const std::uint32_t ld = static_cast<std::uint32_t>(sv->ld);
+    if (kp.kernel == pb::K_LINEAR) {
+        pb::linear_predict_kernel<T><<<static_cast<unsigned>((m + 7) / 8), 256, 0, ctx->stream>>>(P, m, ld, w_d, rho, out_d);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+        return;
+    }
+    TileParams<T> p{};
+    p.A = P;
+    p.B = static_cast<const T *>(sv->X);
+    p.n_rows = static_cast<std::uint32_t>(m);
+    p.n_cols = static_cast<std::uint32_t>(sv->N);
+    p.ld = ld;
+    p.T_rows = (p.n_rows + TILE - 1) / TILE;
+    p.T_cols = (p.n_cols + TILE - 1) / TILE;
+    p.tile_lo = 0;
+    p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
+    p.row_sq = P_sq;
+    p.col_sq = static_cast<const T *>(sv->sq);
+    p.v = alpha_d;
+    p.kp = kp;
+    const std::size_t need = static_cast<std::size_t>(p.T_rows) * p.T_cols * TILE;
+    if (partial.count < need) { partial.alloc(need); }
+    p.partial = partial.p;
+    const bool timed = ctx->tile_timer.begin(ctx->stream);
+    launch_tiles<T, pb::MODE_RECT>(ctx, p);
+    if (timed) { ctx->tile_timer.end(ctx->stream); }
+    pb::reduce_partials_kernel<T, pb::MODE_RECT><<<p.T_rows, 512, 0, ctx->stream>>>(partial.p, out_d, p.n_rows, p.T_rows, p.T_cols, 0, p.tile_hi, 0, T(1), -rho, 0, nullptr);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+}
+
+constexpr std::size_t PREDICT_BATCH = 32768;  // test points per pass (bounds the partial buffer: T_rows x T_cols x 128 values)
+
+template <typename T>
+void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alpha, const T rho, T *w_inout, int *w_valid, const plssvm_b200_dataset *pts_ds, const T *pts_host,
+                    const std::size_t m, const int kernel, const int degree, const T gamma, const T coef0, T *out, const bool with_rho) {
+    check_dataset(ctx, sv, sizeof(T), "support vector");
+    PB_REQUIRE(alpha != nullptr && out != nullptr, "alpha and out must not be NULL");
+    PB_REQUIRE(m > 0, "The data points to predict must not be empty!");
+    validate_kernel_args(kernel, static_cast<double>(gamma));
+    if (pts_ds != nullptr) {
+        check_dataset(ctx, pts_ds, sizeof(T), "predict points");
+        PB_REQUIRE(pts_ds->d == sv->d, "The number of features in the support vectors (" + std::to_string(sv->d) + ") must be the same as in the data points to predict (" +
+                                           std::to_string(pts_ds->d) + ")!");
+    }
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const KernelParams<T> kp{ kernel, degree, gamma, coef0 };
+    const T shift_rho = with_rho ? rho : T(0);
+
+    dbuf<T> alpha_d(sv->N), w_d, out_d(std::min(m, PREDICT_BATCH)), partial;
+    PB_CUDA(cudaMemcpyAsync(alpha_d.p, alpha, sv->N * sizeof(T), cudaMemcpyHostToDevice, st));
+    ctx->tm.h2d_bytes += static_cast<double>(sv->N * sizeof(T));
+    if (kernel == pb::K_LINEAR) {
+        w_d.alloc(sv->ld);
+        if (w_valid != nullptr && *w_valid != 0 && w_inout != nullptr) {
+            PB_CUDA(cudaMemsetAsync(w_d.p, 0, sv->ld * sizeof(T), st));
+            PB_CUDA(cudaMemcpyAsync(w_d.p, w_inout, sv->d * sizeof(T), cudaMemcpyHostToDevice, st));
+        } else {
+            run_w_kernel<T>(ctx, sv, alpha_d.p, w_d.p);
+            if (w_inout != nullptr) {
+                PB_CUDA(cudaMemcpyAsync(w_inout, w_d.p, sv->d * sizeof(T), cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaStreamSynchronize(st));
+                if (w_valid != nullptr) { *w_valid = 1; }
+            }
+        }
+    }
+
+    // host points are staged batch by batch (64-bit offsets; the reference's int indexing overflows here: predict_kernel.cu:40-42)
+    dbuf<T> stage_X, stage_sq;
+    if (pts_ds == nullptr) {
+        stage_X.alloc(std::min(m, PREDICT_BATCH) * sv->ld);
+        stage_sq.alloc(std::min(m, PREDICT_BATCH));
+    }
+    for (std::size_t p0 = 0; p0 < m; p0 += PREDICT_BATCH) {
+        const std::size_t mb = std::min(PREDICT_BATCH, m - p0);
+        const T *P;
+        const T *P_sq;
+        if (pts_ds != nullptr) {
+            P = static_cast<const T *>(pts_ds->X) + p0 * pts_ds->ld;
+            P_sq = static_cast<const T *>(pts_ds->sq) + p0;
+        } else {
+            if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X.p, 0, mb * sv->ld * sizeof(T), st)); }
+            PB_CUDA(cudaMemcpy2DAsync(stage_X.p, sv->ld * sizeof(T), pts_host + p0 * sv->d, sv->d * sizeof(T), sv->d * sizeof(T), mb, cudaMemcpyHostToDevice, st));
+            ctx->tm.h2d_bytes += static_cast<double>(mb * sv->d * sizeof(T));
+            if (kernel == pb::K_RBF) {
+                pb::row_norms_kernel<T><<<static_cast<unsigned>((mb + 7) / 8), 256, 0, st>>>(stage_X.p, mb, static_cast<std::uint32_t>(sv->ld), stage_sq.p);
+                PB_CUDA(cudaGetLastError());
+                ctx->tm.kernel_launches++;
+            }
+            P = stage_X.p;
+            P_sq = stage_sq.p;
+        }
+        predict_rows_device<T>(ctx, sv, alpha_d.p, w_d.p, shift_rho, P, P_sq, mb, kp, out_d.p, partial);
+        PB_CUDA(cudaMemcpyAsync(out + p0, out_d.p, mb * sizeof(T), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        ctx->tm.d2h_bytes += static_cast<double>(mb * sizeof(T));
+    }
+    ctx->tm.matvec_tile_ms = ctx->tile_timer.total_ms();
+}
+
+template <typename F>
+int guarded(F &&f) {
+    try {
+        f();
+        return PLSSVM_B200_OK;
+    } catch (const api_error &e) {
+        g_last_error = e.what();
+        return e.code;
+    } catch (const std::exception &e) {
+        g_last_error = e.what();
+        return PLSSVM_B200_ERR_INTERNAL;
+    }
+}
+
+struct host_timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double ms() const { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// kernel-granular helpers ------------------------------------------------------------------------------------------------------
+template <typename T>
+void api_q_kernel(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const int kernel, const int degree, const T gamma, const T coef0, T *q_out, T *k_last) {
+    check_dataset(ctx, X, sizeof(T), "training");
+    PB_REQUIRE(X->N >= 2 && q_out != nullptr, "q_kernel needs at least two data points and an output buffer");
+    validate_kernel_args(kernel, static_cast<double>(gamma));
+    PB_CUDA(cudaSetDevice(ctx->device));
+    dbuf<T> q_full(X->N);
+    run_q_kernel<T>(ctx, X, KernelParams<T>{ kernel, degree, gamma, coef0 }, q_full.p);
+    PB_CUDA(cudaMemcpyAsync(q_out, q_full.p, (X->N - 1) * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    T last{};
+    PB_CUDA(cudaMemcpyAsync(&last, q_full.p + (X->N - 1), sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (k_last != nullptr) { *k_last = last; }
+}
+
+template <typename T>
+void api_matvec(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *q, const T *v, const T QA_cost, const T cost_inv, const T add, const int kernel, const int degree,
+                const T gamma, const T coef0, T *ret_inout) {
+    check_dataset(ctx, X, sizeof(T), "training");
+    PB_REQUIRE(X->N >= 2, "The data must contain at least two data points!");
+    PB_REQUIRE(q != nullptr && v != nullptr && ret_inout != nullptr, "q, v and ret must not be NULL");
+    PB_REQUIRE(add == T(1) || add == T(-1), "add must either be -1.0 or 1.0, but is " + std::to_string(add) + "!");
+    PB_REQUIRE(cost_inv != T(0), "cost must not be 0.0 since it is 1 / plssvm::cost!");
+    validate_kernel_args(kernel, static_cast<double>(gamma));
+    PB_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const std::uint32_t n = static_cast<std::uint32_t>(X->N - 1);
+    dbuf<T> q_d(n), v_d(n), ret_d(n), out_d(n), qa_d(1);
+    PB_CUDA(cudaMemcpyAsync(q_d.p, q, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(v_d.p, v, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(ret_d.p, ret_inout, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    PB_CUDA(cudaMemcpyAsync(qa_d.p, &QA_cost, sizeof(T), cudaMemcpyHostToDevice, st));
+    matvec_plan<T> mv(ctx, X, KernelParams<T>{ kernel, degree, gamma, coef0 }, q_d.p, qa_d.p, cost_inv, nullptr);
+    ctx->tm.matvec_flops = static_cast<double>(X->d) * static_cast<double>(n) * (static_cast<double>(n) + 1.0);
+    mv.run(v_d.p, out_d.p);
+    pb::axpy_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(ret_d.p, out_d.p, add, n);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+    PB_CUDA(cudaMemcpyAsync(ret_inout, ret_d.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    ctx->tm.matvec_tile_ms = ctx->tile_timer.total_ms();
+    ctx->tm.matvec_ms = ctx->matvec_timer.total_ms();
+}
+
+template <typename T>
+void api_w_kernel(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, T *w_out) {
+    check_dataset(ctx, SV, sizeof(T), "support vector");
+    PB_REQUIRE(alpha != nullptr && w_out != nullptr, "alpha and w_out must not be NULL");
+    PB_CUDA(cudaSetDevice(ctx->device));
+    dbuf<T> alpha_d(SV->N), w_d(SV->ld);
+    PB_CUDA(cudaMemcpyAsync(alpha_d.p, alpha, SV->N * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    run_w_kernel<T>(ctx, SV, alpha_d.p, w_d.p);
+    PB_CUDA(cudaMemcpyAsync(w_out, w_d.p, SV->d * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+
+// ================================================================================================================================
+//                                                           C ABI
+// ================================================================================================================================
+extern "C" {
+
+const char *plssvm_b200_last_error(void) { return g_last_error.c_str(); }
+
+int plssvm_b200_device_count(int *count) {
+    return guarded([&] {
+        PB_REQUIRE(count != nullptr, "count is NULL");
+        PB_CUDA(cudaGetDeviceCount(count));
+    });
+}
+
+int plssvm_b200_create(int device, plssvm_b200_ctx **out) {
+    return guarded([&] {
+        PB_REQUIRE(out != nullptr, "out is NULL");
+        int count = 0;
+        PB_CUDA(cudaGetDeviceCount(&count));
+        if (count == 0) { throw api_error(PLSSVM_B200_ERR_CUDA, "CUDA backend selected but no CUDA devices were found!"); }
+        PB_REQUIRE(device >= 0 && device < count, "invalid device index " + std::to_string(device));
+        PB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop{};
+        PB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10) {
+            throw api_error(PLSSVM_B200_ERR_CUDA, std::string("plssvm_b200 targets sm_100a (B200) only, found '") + prop.name + "' with compute capability " +
+                                                      std::to_string(prop.major) + "." + std::to_string(prop.minor));
+        }
+        auto *ctx = new plssvm_b200_ctx{};
+        ctx->device = device;
+        ctx->num_sms = prop.multiProcessorCount;
+        PB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        PB_CUDA(cudaEventCreate(&ctx->ev_loop0));
+        PB_CUDA(cudaEventCreate(&ctx->ev_loop1));
+        PB_CUDA(cudaMallocHost(&ctx->pinned, 4096));
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres{};
+        PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (fn == nullptr || qres != cudaDriverEntryPointSuccess) { throw api_error(PLSSVM_B200_ERR_CUDA, "driver does not export cuTensorMapEncodeTiled"); }
+        ctx->encode_tiled = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+        *out = ctx;
+    });
+}
+
+int plssvm_b200_destroy(plssvm_b200_ctx *ctx) {
+    return guarded([&] {
+        if (ctx == nullptr) { return; }
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->comm != nullptr) { nccl_api::get().CommDestroy(ctx->comm); }
+        cudaEventDestroy(ctx->ev_loop0);
+        cudaEventDestroy(ctx->ev_loop1);
+        cudaFreeHost(ctx->pinned);
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+    });
+}
+
+int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long value) {
+    return guarded([&] {
+        PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
+        const std::string k(key);
+        if (k == "impl") {
+            PB_REQUIRE(value >= 0 && value <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tensor)");
+            ctx->impl = static_cast<int>(value);
+        } else if (k == "check_interval") {
+            PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");
+            ctx->check_interval = static_cast<int>(value);
+        } else if (k == "verbose") {
+            ctx->verbose = value != 0;
+        } else {
+            throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
+        }
+    });
+}
+
+int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out) {
+    return guarded([&] {
+        PB_REQUIRE(ctx != nullptr && out != nullptr, "ctx or out is NULL");
+        *out = ctx->tm;
+    });
+}
+
+int plssvm_b200_comm_unique_id(void *id128) {
+    return guarded([&] {
+        PB_REQUIRE(id128 != nullptr, "id buffer is NULL");
+        const nccl_api &nccl = nccl_api::get();
+        nccl_api::unique_id id{};
+        nccl.check(nccl.GetUniqueId(&id), "ncclGetUniqueId");
+        std::memcpy(id128, &id, sizeof(id));
+    });
+}
+
+int plssvm_b200_comm_init(plssvm_b200_ctx *ctx, int rank, int world_size, const void *id128) {
+    return guarded([&] {
+        PB_REQUIRE(ctx != nullptr, "context is NULL");
+        PB_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "invalid rank / world size");
+        if (world_size == 1) {
+            ctx->rank = 0;
+            ctx->world = 1;
+            return;
+        }
+        PB_REQUIRE(id128 != nullptr, "id buffer is NULL");
+        PB_CUDA(cudaSetDevice(ctx->device));
+        const nccl_api &nccl = nccl_api::get();
+        nccl_api::unique_id id{};
+        std::memcpy(&id, id128, sizeof(id));
+        nccl.check(nccl.CommInitRank(&ctx->comm, world_size, id, rank), "ncclCommInitRank");
+        ctx->rank = rank;
+        ctx->world = world_size;
+    });
+}
+
+uint64_t plssvm_b200_tile_size(void) { return static_cast<uint64_t>(pb::TILE); }
+uint64_t plssvm_b200_tri_num_tiles(uint64_t tiles_per_side) { return pb::tri_num_tiles(tiles_per_side); }
+uint64_t plssvm_b200_tri_encode(uint64_t tiles_per_side, uint64_t I, uint64_t J) { return pb::tri_encode(tiles_per_side, I, J); }
+void plssvm_b200_tri_decode(uint64_t tiles_per_side, uint64_t L, uint32_t *I, uint32_t *J) { pb::tri_decode(tiles_per_side, L, *I, *J); }
+void plssvm_b200_rank_range(uint64_t total, int rank, int world_size, uint64_t *lo, uint64_t *hi) { pb::rank_range(total, rank, world_size, *lo, *hi); }
+
+int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
+    return guarded([&] {
+        if (ds == nullptr) { return; }
+        cudaSetDevice(ds->ctx->device);
+        cudaFree(ds->X);
+        cudaFree(ds->sq);
+        delete ds;
+    });
+}
+
+#define PB_INSTANTIATE(SUF, T)                                                                                                                                                   \
+    int plssvm_b200_dataset_create_##SUF(plssvm_b200_ctx *ctx, const T *X, size_t N, size_t d, int src_on_device, plssvm_b200_dataset **out) {                                 \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(out != nullptr, "out is NULL");                                                                                                                           \
+            *out = dataset_create<T>(ctx, X, N, d, src_on_device);                                                                                                               \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_solve_dataset_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps, uint64_t max_iter,   \
+                                        T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                                       \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            const host_timer ht;                                                                                                                                                 \
+            reset_timings(ctx);                                                                                                                                                  \
+            solve_dataset<T>(ctx, X, y, kernel, degree, gamma, coef0, cost, eps, max_iter, alpha_out, rho_out, iters_out, residual_out);                                         \
+            ctx->tm.total_ms = ht.ms();                                                                                                                                          \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_solve_##SUF(plssvm_b200_ctx *ctx, const T *X, size_t N, size_t d, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps, uint64_t max_iter,   \
+                                T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                                               \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            const host_timer ht;                                                                                                                                                 \
+            reset_timings(ctx);                                                                                                                                                  \
+            plssvm_b200_dataset *ds = dataset_create<T>(ctx, X, N, d, 0);                                                                                                        \
+            try {                                                                                                                                                                \
+                solve_dataset<T>(ctx, ds, y, kernel, degree, gamma, coef0, cost, eps, max_iter, alpha_out, rho_out, iters_out, residual_out);                                    \
+            } catch (...) {                                                                                                                                                      \
+                plssvm_b200_dataset_destroy(ds);                                                                                                                                 \
+                throw;                                                                                                                                                           \
+            }                                                                                                                                                                    \
+            plssvm_b200_dataset_destroy(ds);                                                                                                                                     \
+            ctx->tm.total_ms = ht.ms();                                                                                                                                          \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_predict_dataset_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, T rho, T *w_inout, int *w_valid, plssvm_b200_dataset *points,          \
+                                          int kernel, int degree, T gamma, T coef0, T *out) {                                                                                   \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr && points != nullptr, "context or points is NULL");                                                                                        \
+            const host_timer ht;                                                                                                                                                 \
+            reset_timings(ctx);                                                                                                                                                  \
+            predict_common<T>(ctx, SV, alpha, rho, w_inout, w_valid, points, nullptr, points->N, kernel, degree, gamma, coef0, out, true);                                       \
+            ctx->tm.total_ms = ht.ms();                                                                                                                                          \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_predict_##SUF(plssvm_b200_ctx *ctx, const T *SV, size_t n_sv, size_t d, const T *alpha, T rho, T *w_inout, int *w_valid, const T *points, size_t m,          \
+                                  int kernel, int degree, T gamma, T coef0, T *out) {                                                                                           \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            PB_REQUIRE(points != nullptr, "The data points to predict must not be empty!");                                                                                      \
+            const host_timer ht;                                                                                                                                                 \
+            reset_timings(ctx);                                                                                                                                                  \
+            plssvm_b200_dataset *ds = dataset_create<T>(ctx, SV, n_sv, d, 0);                                                                                                    \
+            try {                                                                                                                                                                \
+                predict_common<T>(ctx, ds, alpha, rho, w_inout, w_valid, nullptr, points, m, kernel, degree, gamma, coef0, out, true);                                           \
+            } catch (...) {                                                                                                                                                      \
+                plssvm_b200_dataset_destroy(ds);                                                                                                                                 \
+                throw;                                                                                                                                                           \
+            }                                                                                                                                                                    \
+            plssvm_b200_dataset_destroy(ds);                                                                                                                                     \
+            ctx->tm.total_ms = ht.ms();                                                                                                                                          \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_q_kernel_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, int kernel, int degree, T gamma, T coef0, T *q_out, T *k_last) {                               \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            reset_timings(ctx);                                                                                                                                                  \
+            api_q_kernel<T>(ctx, X, kernel, degree, gamma, coef0, q_out, k_last);                                                                                                \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_matvec_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *q, const T *v, T QA_cost, T cost_inv, T add, int kernel, int degree, T gamma, T coef0,  \
+                                 T *ret_inout) {                                                                                                                                 \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            reset_timings(ctx);                                                                                                                                                  \
+            api_matvec<T>(ctx, X, q, v, QA_cost, cost_inv, add, kernel, degree, gamma, coef0, ret_inout);                                                                        \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_w_kernel_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, T *w_out) {                                                                   \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            reset_timings(ctx);                                                                                                                                                  \
+            api_w_kernel<T>(ctx, SV, alpha, w_out);                                                                                                                              \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_predict_kernel_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, plssvm_b200_dataset *points, int kernel, int degree, T gamma, T coef0,  \
+                                         T *out) {                                                                                                                               \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr && points != nullptr, "context or points is NULL");                                                                                        \
+            PB_REQUIRE(kernel != PLSSVM_B200_KERNEL_LINEAR, "run_predict_kernel is only defined for the polynomial and rbf kernels (linear uses run_w_kernel)");                 \
+            reset_timings(ctx);                                                                                                                                                  \
+            predict_common<T>(ctx, SV, alpha, T(0), nullptr, nullptr, points, nullptr, points->N, kernel, degree, gamma, coef0, out, false);                                     \
+        });                                                                                                                                                                      \
+    }
+
+PB_INSTANTIATE(f32, float)
+PB_INSTANTIATE(f64, double)
+
+}  // extern "C"
