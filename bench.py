@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: the implicit kernel-matrix-vector product inside the CG solve of the reduced LS-SVM system.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own OpenMP kernels on the host cores
+
+A *step* is one CG iteration (gpu_csvm.hpp:568-636): one implicit matvec Ad = Q~ d over the whole data set plus the vector
+updates.  Metric = algorithmic matvec TFLOP/s inside the CG loop, F = d * n * (n + 1) FLOPs per iteration;
+`cg_iters_per_s` is the same number expressed per iteration.  Workload at every N: BASELINE.json configs[1],
+65,536 x 4,096 dense, RBF gamma = 1/d, fp64 (strong scaling: tiles of the triangle are sharded over the ranks).
+
+Timing: `value` — data resident in HBM, W untimed + exactly K timed iterations, device time from CUDA events recorded by
+the library on its launching stream, bracketed by barrier + synchronize, max over ranks.  `e2e` — one
+plssvm_b200_solve_f64 call on PINNED HOST buffers (upload of X and y, q-kernel, r0, K iterations, download of alpha).
+X (2.1 GB) is larger than L2 (126 MB) and streamed in full by every iteration, so no explicit L2 flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, d, kernel, dtype, description)
+    "C1": (5000, 1000, "linear", "float64", "5,000 x 1,000 dense, linear, fp64"),
+    "C2": (65536, 4096, "rbf", "float64", "65,536 x 4,096 dense, RBF gamma=1/d, fp64"),
+    "C3": (131072, 1024, "polynomial", "float32", "131,072 x 1,024 dense, polynomial degree 3, fp32"),
+    "C4": (262144, 2048, "linear", "float64", "262,144 x 2,048 dense, linear, fp64"),
+}
+KERNEL_IDS = {"linear": 0, "polynomial": 1, "rbf": 2}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=int, default=0, help="override the number of data points (development only; marks the line as non-headline)")
+    ap.add_argument("--features", type=int, default=0, help="override the number of features (development only)")
+    ap.add_argument("--tile-impl", type=int, default=0, help="0 auto, 1 SIMT tiles, 2 tensor-core tiles")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+def matvec_flops(N: int, d: int) -> float:
+    n = N - 1
+    return float(d) * n * (n + 1)
+
+
+# ---- clocks -----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 100 ms through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self) -> dict:
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---- data -------------------------------------------------------------------------------------------------------------------
+def make_device_data(N, d, dtype, seed, device):
+    """SURVEY.md §8d data family generated on the GPU: X ~ U(-1, 1) + 0.25 y u, balanced +-1 labels in a fixed permutation."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    tdt = {"float64": torch.float64, "float32": torch.float32}[dtype]
+    X = torch.empty((N, d), dtype=tdt, device=device)
+    chunk = max(1, (1 << 28) // d)
+    for r0 in range(0, N, chunk):  # chunked so the fp64 uniform generator never needs a second full-size temporary
+        r1 = min(N, r0 + chunk)
+        X[r0:r1].uniform_(-1.0, 1.0, generator=g)
+    y = torch.ones(N, dtype=tdt, device=device)
+    y[N // 2:] = -1.0
+    y = y[torch.randperm(N, generator=g, device=device)]
+    u = torch.randn(d, generator=g, device=device, dtype=tdt)
+    u /= u.norm()
+    for r0 in range(0, N, chunk):
+        r1 = min(N, r0 + chunk)
+        X[r0:r1] += 0.25 * y[r0:r1, None] * u[None, :]
+    return X, y
+
+
+def make_host_data(N, d, dtype, seed):
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from datagen import make_data
+    return make_data(N, d, seed, np.dtype(dtype))
+
+
+def cpu_matvec_sample(kind_pref, d, kernel, dtype, budget_s, threads=None):
+    """Times the reference's OpenMP matvec (oracle/_ref, else the restated port) on the leading n' rows of the workload."""
+    import numpy as np
+    import oracle
+    kind = kind_pref if oracle.available(kind_pref) else "port"
+    orc = oracle.Oracle(kind)
+    if threads:
+        orc.set_threads(threads)
+    cores = orc.max_threads()
+    kid = KERNEL_IDS[kernel]
+
+    def run(n_rows):
+        X, _ = make_host_data(n_rows + 1, d, dtype, 4242)
+        q = orc.q(kid, X, gamma=1.0 / d)
+        v = np.random.default_rng(1).uniform(1, 2, n_rows).astype(X.dtype)
+        t0 = time.perf_counter()
+        orc.matvec(kid, X, q, v, np.zeros(n_rows, X.dtype), 2.0, 1.0, 1.0, gamma=1.0 / d)
+        return time.perf_counter() - t0
+
+    t_small = run(1024)  # calibration: large enough that all threads get 64x64 blocks
+    rate = d * 1024.0 * 1025.0 / max(t_small, 1e-9)
+    n_rows = int(min(8192, max(512, (budget_s * rate / d) ** 0.5)))
+    n_rows -= n_rows % 64
+    return orc, kind, cores, n_rows, run
+
+
+# ---- reference arm ------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    N, d, kernel, dtype, desc = WORKLOADS[args.workload]
+    d = args.features or d
+    per_step_budget = max(1.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
+    orc, kind, cores, n_rows, run = cpu_matvec_sample("reference", d, kernel, dtype, per_step_budget)
+    for _ in range(args.warmup):
+        run(n_rows)
+    times = [run(n_rows) for _ in range(args.steps)]
+    total = sum(times)
+    F = d * float(n_rows) * (n_rows + 1)
+    value = F * args.steps / total / 1e12
+    sample = f"one OpenMP matvec (the CG iteration's dominant op) per step on the leading {n_rows} rows x {d} features of the workload, all {cores} host threads"
+    line = {
+        "impl": "reference", "metric": "cg_matvec_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32",
+        "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}", "sample_rows": n_rows, "kernel": kernel},
+        "cpu_baseline": {"value": value, "unit": "TFLOP/s", "cores": cores, "kind": "reference" if kind == "reference" else "port", "sample": sample},
+        "e2e": {"value": value, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cg_iters_per_s_extrapolated": value * 1e12 / matvec_flops(N, d), "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- our arm ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import plssvm_b200 as pb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    N, d, kernel, dtype, desc = WORKLOADS[args.workload]
+    headline = not (args.rows or args.features)
+    N, d = args.rows or N, args.features or d
+    F = matvec_flops(N, d)
+    npdt = np.dtype(dtype)
+
+    be = pb.Backend(local_rank)
+    if args.tile_impl:
+        be.set_option("impl", args.tile_impl)
+    if world > 1:
+        be.init_comm_from_torch()
+
+    X, y = make_device_data(N, d, dtype, 42 + list(WORKLOADS).index(args.workload), device)
+    y_host = y.cpu().numpy()
+    ds = be.dataset(X)
+
+    # ---- device-resident timed region: W warm-up + exactly K CG iterations -------------------------------------------------------
+    eps = 1e-30 if dtype == "float64" else 1e-18  # never met: the iteration count is fixed
+    cg = be.cg_begin(ds, y_host, kernel, eps=eps)
+    cg.step(args.warmup)
+    t_before = be.timings()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        done_iters, _ = cg.step(args.steps)
+        barrier()
+        wall = time.perf_counter() - wall0
+    t_after = be.timings()
+    res = cg.finish()
+    dev_ms = t_after["cg_loop_ms"] - t_before["cg_loop_ms"]
+    tile_ms = t_after["matvec_tile_ms"] - t_before["matvec_tile_ms"]
+    tile_calls = t_after["matvec_calls"] - t_before["matvec_calls"]
+    launches = t_after["kernel_launches"] - t_before["kernel_launches"]
+    if world > 1:
+        tt = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, wall = float(tt[0]), float(tt[1]) / 1e3
+    assert done_iters == args.warmup + args.steps, (done_iters, args.warmup, args.steps)
+    value = F * args.steps / (dev_ms * 1e-3) / 1e12
+
+    # ---- end to end through the C ABI with pinned host buffers --------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Xh = torch.empty((N, d), dtype=X.dtype, pin_memory=True)
+        Xh.copy_(X)
+        yh = torch.empty(N, dtype=X.dtype, pin_memory=True)
+        yh.copy_(y)
+        del X
+        torch.cuda.empty_cache()
+        barrier()
+        t0 = time.perf_counter()
+        r2 = be.solve(Xh, yh, kernel, eps=eps, max_iter=args.steps)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([t_e2e], dtype=torch.float64, device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_e2e = float(tt[0])
+        t2 = be.timings()
+        e2e = {"value": F * r2["iterations"] / t_e2e / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": t2["h2d_bytes"] / r2["iterations"],
+               "d2h_bytes_per_step": t2["d2h_bytes"] / r2["iterations"], "seconds": t_e2e, "iterations": r2["iterations"],
+               "note": "one plssvm_b200_solve call: H2D of X and y from pinned memory + q-kernel + r0 matvec + K iterations + D2H of alpha; bytes are per call / K"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the tile kernel) ---------------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
+    peak, peak_src = 37.0, "vendor figure (fallback: profiles/peaks_b200.json missing)"
+    key = "dmma_tflops_sustained_3s" if dtype == "float64" else "ffma_tflops"
+    if os.path.exists(peaks_path):
+        pk = json.load(open(peaks_path))
+        if key in pk:
+            peak, peak_src = float(pk[key]), f"measured on this pool's B200 by tools/peak_probe ({key}; profiles/peaks_b200.json)"
+    avg_tile_s = tile_ms / max(tile_calls, 1) * 1e-3
+    achieved = (F / world) / avg_tile_s / 1e12 if avg_tile_s > 0 else 0.0
+    traffic = None
+    ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(ncu_path):
+        traffic = json.load(open(ncu_path)).get(args.workload)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "tile_kernel_dmma<rbf, sym>" if t_after["impl_used"] == 2 else "tile_kernel_simt", "peak_source": peak_src,
+                "avg_launch_ms": avg_tile_s * 1e3, "launches_timed": int(tile_calls), "flops_per_launch": F / world}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        orc, kind, cores, n_rows, run = cpu_matvec_sample("reference", d, kernel, dtype, args.cpu_seconds)
+        t_cpu = run(n_rows)
+        cpu_baseline = {"value": d * float(n_rows) * (n_rows + 1) / t_cpu / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference" if kind == "reference" else "port",
+                        "sample": f"one OpenMP matvec on the leading {n_rows} rows x {d} features ({t_cpu:.1f} s); same kernel / real type"}
+
+    line = {
+        "metric": "cg_matvec_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}" + ("" if headline else f" [DEV OVERRIDE rows={N} features={d}]"), "kernel": kernel, "rows": N, "features": d,
+                   "flops_per_step": F, "l2": "inputs (2.1 GB) larger than L2; no flush needed", "parallelism": f"triangle tiles sharded over {world} rank(s), X replicated"},
+        "cg_iters_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "final_residual": float(res["delta"]), "tile_impl": int(t_after["impl_used"]),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,6 +102,20 @@ int plssvm_b200_solve_dataset_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, 
 int plssvm_b200_solve_dataset_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const double *y, int kernel, int degree, double gamma, double coef0,
                                   double cost, double eps, uint64_t max_iter, double *alpha_out, double *rho_out, uint64_t *iters_out, double *residual_out);
 
+/* The same solve as a session, for callers that want to drive / time the CG iterations themselves (bench.py times exactly
+ * K iterations with it): begin = upload y, q-kernel, QA_cost, r0 = b~ - Q~ 1, d0 = r0 (gpu_csvm.hpp:505-554);
+ * step = enqueue `iterations` CG iterations (gpu_csvm.hpp:568-636) and poll the device-side state once — iterations past
+ * convergence are no-ops; finish = bias / alpha_N / download (gpu_csvm.hpp:649-653) and frees the session. */
+typedef struct plssvm_b200_cg plssvm_b200_cg;
+int plssvm_b200_cg_begin_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const float *y, int kernel, int degree, float gamma, float coef0, float cost, float eps,
+                             plssvm_b200_cg **out);
+int plssvm_b200_cg_begin_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const double *y, int kernel, int degree, double gamma, double coef0, double cost, double eps,
+                             plssvm_b200_cg **out);
+int plssvm_b200_cg_step(plssvm_b200_cg *cg, uint64_t iterations, uint64_t *iterations_done, int *converged);
+int plssvm_b200_cg_finish_f32(plssvm_b200_cg *cg, float *alpha_out, float *rho_out, uint64_t *iters_out, float *residual_out);
+int plssvm_b200_cg_finish_f64(plssvm_b200_cg *cg, double *alpha_out, double *rho_out, uint64_t *iters_out, double *residual_out);
+int plssvm_b200_cg_abort(plssvm_b200_cg *cg);
+
 /* ---- csvm::predict_values (csvm.hpp:204-208; gpu_csvm.hpp:656-730) --------------------------------------------------
  * out[p] = sum_i alpha_i k(sv_i, point_p) - rho.  Linear kernel: w = sum_i alpha_i sv_i is computed iff *w_valid == 0,
  * stored in w_inout[d] and *w_valid set to 1 (the reference's `w` cache, gpu_csvm.hpp:696-698); other kernels leave

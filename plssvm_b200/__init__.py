@@ -22,7 +22,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["Backend", "Dataset", "CSVM", "Parameter", "Model", "BackendError", "lib_path", "load_library",
+__all__ = ["Backend", "Dataset", "CGSession", "CSVM", "Parameter", "Model", "BackendError", "lib_path", "load_library",
            "LINEAR", "POLYNOMIAL", "RBF", "kernel_id", "tile_size", "tri_num_tiles", "tri_encode", "tri_decode", "rank_range"]
 
 LINEAR, POLYNOMIAL, RBF = 0, 1, 2
@@ -89,10 +89,14 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.plssvm_b200_rank_range.restype = None
     lib.plssvm_b200_rank_range.argtypes = [u64, i32, i32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     lib.plssvm_b200_dataset_destroy.argtypes = [vp]
+    lib.plssvm_b200_cg_step.argtypes = [vp, u64, ctypes.POINTER(u64), ctypes.POINTER(i32)]
+    lib.plssvm_b200_cg_abort.argtypes = [vp]
     for suf, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
         getattr(lib, f"plssvm_b200_dataset_create_{suf}").argtypes = [vp, vp, sz, sz, i32, ctypes.POINTER(vp)]
         getattr(lib, f"plssvm_b200_solve_{suf}").argtypes = [vp, vp, sz, sz, vp, i32, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
         getattr(lib, f"plssvm_b200_solve_dataset_{suf}").argtypes = [vp, vp, vp, i32, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
+        getattr(lib, f"plssvm_b200_cg_begin_{suf}").argtypes = [vp, vp, vp, i32, i32, ct, ct, ct, ct, ctypes.POINTER(vp)]
+        getattr(lib, f"plssvm_b200_cg_finish_{suf}").argtypes = [vp, vp, vp, vp, vp]
         getattr(lib, f"plssvm_b200_predict_{suf}").argtypes = [vp, vp, sz, sz, vp, ct, vp, vp, vp, sz, i32, i32, ct, ct, vp]
         getattr(lib, f"plssvm_b200_predict_dataset_{suf}").argtypes = [vp, vp, vp, ct, vp, vp, vp, i32, i32, ct, ct, vp]
         getattr(lib, f"plssvm_b200_q_kernel_{suf}").argtypes = [vp, vp, i32, i32, ct, ct, vp, vp]
@@ -107,9 +111,9 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "plssvm_b200_create", "plssvm_b200_destroy", "plssvm_b200_last_error", "plssvm_b200_set_option", "plssvm_b200_get_timings", "plssvm_b200_device_count",
     "plssvm_b200_comm_unique_id", "plssvm_b200_comm_init", "plssvm_b200_tile_size", "plssvm_b200_tri_num_tiles", "plssvm_b200_tri_encode", "plssvm_b200_tri_decode",
-    "plssvm_b200_rank_range", "plssvm_b200_dataset_destroy",
+    "plssvm_b200_rank_range", "plssvm_b200_dataset_destroy", "plssvm_b200_cg_step", "plssvm_b200_cg_abort",
 ] + [f"plssvm_b200_{name}_{suf}" for suf in ("f32", "f64")
-     for name in ("dataset_create", "solve", "solve_dataset", "predict", "predict_dataset", "q_kernel", "matvec", "w_kernel", "predict_kernel")]
+     for name in ("dataset_create", "solve", "solve_dataset", "cg_begin", "cg_finish", "predict", "predict_dataset", "q_kernel", "matvec", "w_kernel", "predict_kernel")]
 
 
 def _check(rc: int) -> None:
@@ -291,6 +295,10 @@ class Backend:
             _check(fn(self._h, _ptr(X), N, d, _ptr(yh), k, int(degree), gamma, coef0, cost, eps, max_iter, _ptr(alpha), _ptr(rho), _ptr(iters), _ptr(res)))
         return {"alpha": alpha, "rho": rho[0], "iterations": int(iters[0]), "delta": res[0], "delta0": res[1]}
 
+    def cg_begin(self, X: "Dataset", y, kernel, *, degree=3, gamma=None, coef0=0.0, cost=1.0, eps=1e-3) -> "CGSession":
+        """The same solve as a session whose iterations the caller drives (bench.py times exactly K of them)."""
+        return CGSession(self, X, y, kernel, degree=degree, gamma=gamma, coef0=coef0, cost=cost, eps=eps)
+
     # -- csvm::predict_values ----------------------------------------------------------------------------------------------------
     def predict_values(self, SV, alpha, rho, points, kernel, *, degree=3, gamma=None, coef0=0.0, w=None):
         """Returns (values[m], w) — ``w`` is the linear-kernel normal vector (filled iff kernel is linear), else None."""
@@ -364,6 +372,46 @@ class Backend:
         out = np.empty(points.N, dtype=SV.dtype)
         _check(getattr(self.lib, f"plssvm_b200_predict_kernel_{suf}")(self._h, SV._h, _ptr(alpha), points._h, kernel_id(kernel), int(degree), gamma, coef0, _ptr(out)))
         return out
+
+
+class CGSession:
+    """begin / step / finish of one CG solve on a resident dataset (plssvm_b200_cg_*)."""
+
+    def __init__(self, backend: Backend, X: Dataset, y, kernel, *, degree=3, gamma=None, coef0=0.0, cost=1.0, eps=1e-3):
+        self.backend, self.X = backend, X
+        self._h = ctypes.c_void_p()
+        self.suf = _suffix(X.dtype)
+        yh = _host(y, X.dtype)
+        if yh.shape != (X.N,):
+            raise ValueError("label vector has the wrong length")
+        gamma = 1.0 / X.d if gamma is None else gamma
+        _check(getattr(backend.lib, f"plssvm_b200_cg_begin_{self.suf}")(backend._h, X._h, _ptr(yh), kernel_id(kernel), int(degree), gamma, coef0, cost, eps, ctypes.byref(self._h)))
+
+    def step(self, iterations: int):
+        """Enqueue ``iterations`` CG iterations, wait for them, return (completed iterations, converged)."""
+        done, conv = ctypes.c_uint64(), ctypes.c_int()
+        _check(self.backend.lib.plssvm_b200_cg_step(self._h, int(iterations), ctypes.byref(done), ctypes.byref(conv)))
+        return int(done.value), bool(conv.value)
+
+    def finish(self) -> dict:
+        alpha = np.empty(self.X.N, dtype=self.X.dtype)
+        rho = np.zeros(1, dtype=self.X.dtype)
+        iters = np.zeros(1, dtype=np.uint64)
+        res = np.zeros(2, dtype=self.X.dtype)
+        h, self._h = self._h, ctypes.c_void_p()
+        _check(getattr(self.backend.lib, f"plssvm_b200_cg_finish_{self.suf}")(h, _ptr(alpha), _ptr(rho), _ptr(iters), _ptr(res)))
+        return {"alpha": alpha, "rho": rho[0], "iterations": int(iters[0]), "delta": res[0], "delta0": res[1]}
+
+    def abort(self) -> None:
+        if self._h:
+            self.backend.lib.plssvm_b200_cg_abort(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.abort()
+        except Exception:
+            pass
 
 
 # ---- the reference-facing interface ---------------------------------------------------------------------------------------------

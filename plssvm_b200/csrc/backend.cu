@@ -26,6 +26,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -395,56 +396,84 @@ plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const T *X, const std:
 }
 
 // ---- solve: csvm::solve_system_of_linear_equations (gpu_csvm.hpp:477-654) ----------------------------------------------------
+// One CG solve as a session: begin (b~, x0 = 1, q, QA_cost, r0 = b~ - Q~ x0, d0 = r0), step (k iterations enqueued back to
+// back, then one poll of the device-side state), finish (bias, alpha_N, download).  plssvm_b200_solve_* is begin + step
+// until converged / max_iter + finish; the benchmark drives step() directly so that exactly K iterations are timed.
+struct cg_session_base {
+    plssvm_b200_ctx *ctx = nullptr;
+    int elem_size = 0;
+    virtual ~cg_session_base() = default;
+};
+
 template <typename T>
-void solve_dataset(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const T *y, const int kernel, const int degree, const T gamma, const T coef0, const T cost, const T eps,
-                   const std::uint64_t max_iter, T *alpha_out, T *rho_out, std::uint64_t *iters_out, T *residual_out) {
-    check_dataset(ctx, ds, sizeof(T), "training");
-    PB_REQUIRE(y != nullptr && alpha_out != nullptr && rho_out != nullptr, "y, alpha_out and rho_out must not be NULL");
-    PB_REQUIRE(ds->N >= 2, "The data must contain at least two data points!");
-    PB_REQUIRE(eps > T(0), "The stopping criterion in the CG algorithm must be greater than 0.0, but is " + std::to_string(eps) + "!");
-    PB_REQUIRE(max_iter > 0, "The number of CG iterations must be greater than 0!");
-    PB_REQUIRE(cost != T(0), "cost must not be 0.0!");
-    validate_kernel_args(kernel, static_cast<double>(gamma));
-    PB_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+struct cg_session : cg_session_base {
+    plssvm_b200_dataset *ds;
+    KernelParams<T> kp;
+    T cost, eps;
+    std::uint32_t n;
+    unsigned vblocks;
+    dbuf<T> y_d, q_full, b, x, r, dvec, Ad, part;
+    dbuf<CGState<T>> state;
+    std::unique_ptr<matvec_plan<T>> mv;
+    std::uint64_t iters_enqueued = 0;
+    bool converged = false;
+    CGState<T> last{};  // last polled copy of the device state
 
-    const std::size_t N = ds->N;
-    const std::uint32_t n = static_cast<std::uint32_t>(N - 1);
-    const KernelParams<T> kp{ kernel, degree, gamma, coef0 };
-    const unsigned vblocks = (n + pb::VEC_CHUNK - 1) / pb::VEC_CHUNK;
+    cg_session(plssvm_b200_ctx *c, plssvm_b200_dataset *data, const T *y, const int kernel, const int degree, const T gamma, const T coef0, const T cost_, const T eps_) :
+        ds(data), kp{ kernel, degree, gamma, coef0 }, cost(cost_), eps(eps_) {
+        ctx = c;
+        elem_size = static_cast<int>(sizeof(T));
+        check_dataset(ctx, ds, sizeof(T), "training");
+        PB_REQUIRE(y != nullptr, "y must not be NULL");
+        PB_REQUIRE(ds->N >= 2, "The data must contain at least two data points!");
+        PB_REQUIRE(eps > T(0), "The stopping criterion in the CG algorithm must be greater than 0.0, but is " + std::to_string(eps) + "!");
+        PB_REQUIRE(cost != T(0), "cost must not be 0.0!");
+        validate_kernel_args(kernel, static_cast<double>(gamma));
+        PB_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        const std::size_t N = ds->N;
+        n = static_cast<std::uint32_t>(N - 1);
+        vblocks = (n + pb::VEC_CHUNK - 1) / pb::VEC_CHUNK;
+        y_d.alloc(N);
+        q_full.alloc(N);
+        b.alloc(n);
+        x.alloc(n);
+        r.alloc(n);
+        dvec.alloc(n);
+        Ad.alloc(n);
+        part.alloc(vblocks);
+        state.alloc(1);
 
-    dbuf<T> y_d(N), q_full(N), b(n), x(n), r(n), dvec(n), Ad(n), part(vblocks);
-    dbuf<CGState<T>> state(1);
-    CGState<T> *h_state = static_cast<CGState<T> *>(ctx->pinned);
-    const int *done = &state.p->done;
+        PB_CUDA(cudaMemcpyAsync(y_d.p, y, N * sizeof(T), cudaMemcpyHostToDevice, st));
+        ctx->tm.h2d_bytes += static_cast<double>(N * sizeof(T));
+        PB_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CGState<T>), st));
+        pb::cg_init_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(y_d.p, n, b.p, x.p, state.p, cost);
+        run_q_kernel<T>(ctx, ds, kp, q_full.p);
+        pb::cg_qa_cost_kernel<T><<<1, 1, 0, st>>>(q_full.p, n, state.p, cost);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches += 2;
 
-    PB_CUDA(cudaMemcpyAsync(y_d.p, y, N * sizeof(T), cudaMemcpyHostToDevice, st));
-    ctx->tm.h2d_bytes += static_cast<double>(N * sizeof(T));
-    PB_CUDA(cudaMemsetAsync(state.p, 0, sizeof(CGState<T>), st));
-    pb::cg_init_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(y_d.p, n, b.p, x.p, state.p, cost);
-    run_q_kernel<T>(ctx, ds, kp, q_full.p);
-    pb::cg_qa_cost_kernel<T><<<1, 1, 0, st>>>(q_full.p, n, state.p, cost);
-    PB_CUDA(cudaGetLastError());
-    ctx->tm.kernel_launches += 2;
+        mv = std::make_unique<matvec_plan<T>>(ctx, ds, kp, q_full.p, &state.p->QA_cost, T(1) / cost, &state.p->done);
+        ctx->tm.matvec_flops = static_cast<double>(ds->d) * static_cast<double>(n) * (static_cast<double>(n) + 1.0);
 
-    matvec_plan<T> mv(ctx, ds, kp, q_full.p, &state.p->QA_cost, T(1) / cost, done);
-    ctx->tm.matvec_flops = static_cast<double>(ds->d) * static_cast<double>(n) * (static_cast<double>(n) + 1.0);
+        // r = b - Q~ x0,  delta0 = r.r,  d = r     (gpu_csvm.hpp:515-554)
+        mv->run(x.p, Ad.p);
+        pb::cg_residual_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(b.p, Ad.p, r.p, n, part.p, nullptr);
+        pb::cg_start_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p);
+        pb::cg_update_d_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches += 3;
+    }
 
-    // r = b - Q~ x0,  delta0 = r.r,  d = r     (gpu_csvm.hpp:515-554)
-    mv.run(x.p, Ad.p);
-    pb::cg_residual_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(b.p, Ad.p, r.p, n, part.p, nullptr);
-    pb::cg_start_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p);
-    pb::cg_update_d_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);
-    PB_CUDA(cudaGetLastError());
-    ctx->tm.kernel_launches += 3;
-
-    const auto enqueue_iteration = [&](const std::uint64_t iter) {
-        mv.run(dvec.p, Ad.p);                                                                                       // Ad = Q~ d        (574-582)
+    void enqueue_iteration(const std::uint64_t iter) {
+        cudaStream_t st = ctx->stream;
+        const int *done = &state.p->done;
+        mv->run(dvec.p, Ad.p);                                                                                       // Ad = Q~ d        (574-582)
         pb::dot_partial_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, Ad.p, n, part.p, done);
         pb::cg_alpha_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p);                               // alpha = delta / d.Ad (585)
         if (iter % 50 == 49) {                                                                                      // residual refresh (595-609)
             pb::cg_update_xr_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(x.p, r.p, dvec.p, Ad.p, n, state.p, part.p);
-            mv.run(x.p, Ad.p);
+            mv->run(x.p, Ad.p);
             pb::cg_residual_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(b.p, Ad.p, r.p, n, part.p, done);
         } else {
             pb::cg_update_xr_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(x.p, r.p, dvec.p, Ad.p, n, state.p, part.p);  // x += a d; r -= a Ad (588, 611-613)
@@ -453,49 +482,68 @@ void solve_dataset(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const T *y, co
         pb::cg_update_d_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);                // d = beta d + r   (627)
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += (iter % 50 == 49) ? 6 : 5;
-    };
-
-    // host only polls: every `interval` iterations one 100-byte read-back; kernels of iterations enqueued past convergence exit at once
-    std::uint64_t interval = ctx->check_interval > 0 ? static_cast<std::uint64_t>(ctx->check_interval) : (n >= 16384 ? 1 : 8);
-    PB_CUDA(cudaEventRecord(ctx->ev_loop0, st));
-    std::uint64_t it = 0;
-    while (it < max_iter) {
-        const std::uint64_t batch = std::min<std::uint64_t>(interval, max_iter - it);
-        for (std::uint64_t k = 0; k < batch; ++k) { enqueue_iteration(it + k); }
-        it += batch;
-        PB_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CGState<T>), cudaMemcpyDeviceToHost, st));
-        PB_CUDA(cudaStreamSynchronize(st));
-        if (ctx->verbose != 0) {
-            std::printf("[plssvm_b200] iteration %llu (max: %llu) residuum %g (target: %g)\n", static_cast<unsigned long long>(h_state->iter),
-                        static_cast<unsigned long long>(max_iter), static_cast<double>(h_state->delta), static_cast<double>(eps * eps * h_state->delta0));
-        }
-        if (h_state->done != 0) { break; }
     }
-    PB_CUDA(cudaEventRecord(ctx->ev_loop1, st));
+
+    // enqueue `count` iterations back to back, then poll the device state once (one ~100-byte read-back + sync).
+    // Kernels of iterations enqueued past convergence exit immediately (device-side `done` flag), so x is never over-updated.
+    void step(const std::uint64_t count) {
+        PB_CUDA(cudaSetDevice(ctx->device));
+        if (converged) { return; }
+        PB_CUDA(cudaEventRecord(ctx->ev_loop0, ctx->stream));
+        for (std::uint64_t k = 0; k < count; ++k) { enqueue_iteration(iters_enqueued + k); }
+        PB_CUDA(cudaEventRecord(ctx->ev_loop1, ctx->stream));
+        iters_enqueued += count;
+        poll();
+        float ms = 0.f;
+        PB_CUDA(cudaEventElapsedTime(&ms, ctx->ev_loop0, ctx->ev_loop1));
+        ctx->tm.cg_loop_ms += ms;  // device time of the iterations alone (events on the launching stream)
+    }
+
+    void poll() {
+        CGState<T> *h_state = static_cast<CGState<T> *>(ctx->pinned);
+        PB_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CGState<T>), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        last = *h_state;
+        converged = last.done != 0;
+        if (ctx->verbose != 0) {
+            std::printf("[plssvm_b200] iteration %llu residuum %g (target: %g)\n", static_cast<unsigned long long>(last.iter), static_cast<double>(last.delta),
+                        static_cast<double>(eps * eps * last.delta0));
+        }
+    }
 
     // bias and the last alpha (gpu_csvm.hpp:649-653)
-    pb::cg_finish_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(x.p, q_full.p, n, state.p);
-    PB_CUDA(cudaGetLastError());
-    ctx->tm.kernel_launches++;
-    PB_CUDA(cudaMemcpyAsync(h_state, state.p, sizeof(CGState<T>), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaMemcpyAsync(alpha_out, x.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(cudaStreamSynchronize(st));
-    ctx->tm.d2h_bytes += static_cast<double>(n * sizeof(T));
-    alpha_out[n] = -h_state->sum_x;
-    *rho_out = -h_state->bias;
-    if (iters_out != nullptr) { *iters_out = std::min<std::uint64_t>(h_state->iter, max_iter); }
-    if (residual_out != nullptr) {
-        residual_out[0] = h_state->delta;
-        residual_out[1] = h_state->delta0;
+    void finish(T *alpha_out, T *rho_out, std::uint64_t *iters_out, T *residual_out) {
+        PB_REQUIRE(alpha_out != nullptr && rho_out != nullptr, "alpha_out and rho_out must not be NULL");
+        PB_CUDA(cudaSetDevice(ctx->device));
+        cudaStream_t st = ctx->stream;
+        pb::cg_finish_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(x.p, q_full.p, n, state.p);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+        PB_CUDA(cudaMemcpyAsync(alpha_out, x.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+        ctx->tm.d2h_bytes += static_cast<double>(n * sizeof(T));
+        poll();
+        alpha_out[n] = -last.sum_x;
+        *rho_out = -last.bias;
+        if (iters_out != nullptr) { *iters_out = last.iter; }
+        if (residual_out != nullptr) {
+            residual_out[0] = last.delta;
+            residual_out[1] = last.delta0;
+        }
+        if (ctx->verbose != 0) { std::printf("[plssvm_b200] optimization finished, #iter = %llu\n", static_cast<unsigned long long>(last.iter)); }
+        ctx->tm.matvec_tile_ms = ctx->tile_timer.total_ms();
+        ctx->tm.matvec_ms = ctx->matvec_timer.total_ms();
     }
-    if (ctx->verbose != 0) {
-        std::printf("[plssvm_b200] optimization finished, #iter = %llu\n", static_cast<unsigned long long>(std::min<std::uint64_t>(h_state->iter, max_iter)));
-    }
-    float loop_ms = 0.f;
-    PB_CUDA(cudaEventElapsedTime(&loop_ms, ctx->ev_loop0, ctx->ev_loop1));
-    ctx->tm.cg_loop_ms = loop_ms;
-    ctx->tm.matvec_tile_ms = ctx->tile_timer.total_ms();
-    ctx->tm.matvec_ms = ctx->matvec_timer.total_ms();
+};
+
+template <typename T>
+void solve_dataset(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const T *y, const int kernel, const int degree, const T gamma, const T coef0, const T cost, const T eps,
+                   const std::uint64_t max_iter, T *alpha_out, T *rho_out, std::uint64_t *iters_out, T *residual_out) {
+    PB_REQUIRE(max_iter > 0, "The number of CG iterations must be greater than 0!");
+    PB_REQUIRE(alpha_out != nullptr && rho_out != nullptr, "alpha_out and rho_out must not be NULL");
+    cg_session<T> cg(ctx, ds, y, kernel, degree, gamma, coef0, cost, eps);
+    const std::uint64_t interval = ctx->check_interval > 0 ? static_cast<std::uint64_t>(ctx->check_interval) : (cg.n >= 16384 ? 1 : 8);
+    while (cg.iters_enqueued < max_iter && !cg.converged) { cg.step(std::min<std::uint64_t>(interval, max_iter - cg.iters_enqueued)); }
+    cg.finish(alpha_out, rho_out, iters_out, residual_out);
 }
 
 // ---- w-kernel -----------------------------------------------------------------------------------------------------------------
@@ -827,11 +875,63 @@ int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
     });
 }
 
+struct plssvm_b200_cg {
+    std::unique_ptr<cg_session_base> impl;
+};
+
+int plssvm_b200_cg_step(plssvm_b200_cg *cg, uint64_t iterations, uint64_t *iterations_done, int *converged) {
+    return guarded([&] {
+        PB_REQUIRE(cg != nullptr && cg->impl != nullptr, "cg session is NULL");
+        if (cg->impl->elem_size == 8) {
+            auto *s = static_cast<cg_session<double> *>(cg->impl.get());
+            s->step(iterations);
+            if (iterations_done != nullptr) { *iterations_done = s->last.iter; }
+            if (converged != nullptr) { *converged = s->converged ? 1 : 0; }
+        } else {
+            auto *s = static_cast<cg_session<float> *>(cg->impl.get());
+            s->step(iterations);
+            if (iterations_done != nullptr) { *iterations_done = s->last.iter; }
+            if (converged != nullptr) { *converged = s->converged ? 1 : 0; }
+        }
+        cg->impl->ctx->tm.matvec_tile_ms = cg->impl->ctx->tile_timer.total_ms();
+        cg->impl->ctx->tm.matvec_ms = cg->impl->ctx->matvec_timer.total_ms();
+    });
+}
+
+int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
+    return guarded([&] {
+        if (cg == nullptr) { return; }
+        if (cg->impl != nullptr) {
+            cudaSetDevice(cg->impl->ctx->device);
+            cudaStreamSynchronize(cg->impl->ctx->stream);
+        }
+        delete cg;
+    });
+}
+
 #define PB_INSTANTIATE(SUF, T)                                                                                                                                                   \
     int plssvm_b200_dataset_create_##SUF(plssvm_b200_ctx *ctx, const T *X, size_t N, size_t d, int src_on_device, plssvm_b200_dataset **out) {                                 \
         return guarded([&] {                                                                                                                                                     \
             PB_REQUIRE(out != nullptr, "out is NULL");                                                                                                                           \
             *out = dataset_create<T>(ctx, X, N, d, src_on_device);                                                                                                               \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_cg_begin_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps, plssvm_b200_cg **out) { \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(ctx != nullptr && out != nullptr, "context or out is NULL");                                                                                              \
+            reset_timings(ctx);                                                                                                                                                  \
+            auto holder = std::make_unique<plssvm_b200_cg>();                                                                                                                    \
+            holder->impl = std::make_unique<cg_session<T>>(ctx, X, y, kernel, degree, gamma, coef0, cost, eps);                                                                  \
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));                                                                                                                         \
+            *out = holder.release();                                                                                                                                             \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_cg_finish_##SUF(plssvm_b200_cg *cg, T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                       \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(cg != nullptr && cg->impl != nullptr, "cg session is NULL");                                                                                              \
+            PB_REQUIRE(cg->impl->elem_size == static_cast<int>(sizeof(T)), "cg session has the wrong real_type");                                                                \
+            static_cast<cg_session<T> *>(cg->impl.get())->finish(alpha_out, rho_out, iters_out, residual_out);                                                                   \
+            delete cg;                                                                                                                                                           \
         });                                                                                                                                                                      \
     }                                                                                                                                                                            \
     int plssvm_b200_solve_dataset_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps, uint64_t max_iter,   \

@@ -11,6 +11,7 @@ import pytest
 
 import oracle
 from datagen import GOLDEN_CASES, make_case
+from parity import check_solution
 
 KERNELS = {"linear": 0, "polynomial": 1, "rbf": 2}
 
@@ -121,12 +122,7 @@ def test_port_matches_reference_vectors(port, case, golden_dir):
     # first residuals must agree tightly (before CG has amplified the rounding noise)
     assert np.allclose(res["trace"][:2], g[f"{name}/trace"][:2], rtol=1e-9 if X.dtype == np.float64 else 1e-3)
     if res["iterations"] == int(g[f"{name}/iterations"]):
-        # tolerance: the stated one (1e-10 fp64 / 1e-4 fp32), widened to 20x the reference's own run-to-run spread
-        base = 1e-10 if X.dtype == np.float64 else 1e-4
-        atol_a = max(base, 20 * float(g[f"{name}/alpha_spread"]))
-        scale = np.max(np.abs(g[f"{name}/alpha"]))
-        assert np.max(np.abs(res["alpha"] - g[f"{name}/alpha"])) <= atol_a * scale
-        assert abs(res["rho"] - float(g[f"{name}/rho"])) <= max(base * scale, 20 * float(g[f"{name}/rho_spread"]), atol_a * scale)
+        check_solution(res["alpha"], res["rho"], g[f"{name}/alpha"], float(g[f"{name}/rho"]), X.dtype, spread=float(g[f"{name}/alpha_spread"]), qa_cost=qa, tag=name)
     vals, _ = port.predict(k, X, g[f"{name}/alpha"], float(g[f"{name}/rho"]), c["P"], **pr)
     assert (oracle.sign_labels(vals) == oracle.sign_labels(g[f"{name}/predict"])).all()
 
