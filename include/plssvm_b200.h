@@ -112,6 +112,9 @@ int plssvm_b200_cg_begin_f32(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const
 int plssvm_b200_cg_begin_f64(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const double *y, int kernel, int degree, double gamma, double coef0, double cost, double eps,
                              plssvm_b200_cg **out);
 int plssvm_b200_cg_step(plssvm_b200_cg *cg, uint64_t iterations, uint64_t *iterations_done, int *converged);
+/* residual history: out[k] = r.r after k iterations (k = 0 is r0.r0); *count entries written (<= capacity, <= 4097) */
+int plssvm_b200_cg_trace_f32(plssvm_b200_cg *cg, float *out, size_t capacity, size_t *count);
+int plssvm_b200_cg_trace_f64(plssvm_b200_cg *cg, double *out, size_t capacity, size_t *count);
 int plssvm_b200_cg_finish_f32(plssvm_b200_cg *cg, float *alpha_out, float *rho_out, uint64_t *iters_out, float *residual_out);
 int plssvm_b200_cg_finish_f64(plssvm_b200_cg *cg, double *alpha_out, double *rho_out, uint64_t *iters_out, double *residual_out);
 int plssvm_b200_cg_abort(plssvm_b200_cg *cg);

@@ -97,6 +97,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         getattr(lib, f"plssvm_b200_solve_dataset_{suf}").argtypes = [vp, vp, vp, i32, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
         getattr(lib, f"plssvm_b200_cg_begin_{suf}").argtypes = [vp, vp, vp, i32, i32, ct, ct, ct, ct, ctypes.POINTER(vp)]
         getattr(lib, f"plssvm_b200_cg_finish_{suf}").argtypes = [vp, vp, vp, vp, vp]
+        getattr(lib, f"plssvm_b200_cg_trace_{suf}").argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
         getattr(lib, f"plssvm_b200_predict_{suf}").argtypes = [vp, vp, sz, sz, vp, ct, vp, vp, vp, sz, i32, i32, ct, ct, vp]
         getattr(lib, f"plssvm_b200_predict_dataset_{suf}").argtypes = [vp, vp, vp, ct, vp, vp, vp, i32, i32, ct, ct, vp]
         getattr(lib, f"plssvm_b200_q_kernel_{suf}").argtypes = [vp, vp, i32, i32, ct, ct, vp, vp]
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = [
     "plssvm_b200_comm_unique_id", "plssvm_b200_comm_init", "plssvm_b200_tile_size", "plssvm_b200_tri_num_tiles", "plssvm_b200_tri_encode", "plssvm_b200_tri_decode",
     "plssvm_b200_rank_range", "plssvm_b200_dataset_destroy", "plssvm_b200_cg_step", "plssvm_b200_cg_abort",
 ] + [f"plssvm_b200_{name}_{suf}" for suf in ("f32", "f64")
-     for name in ("dataset_create", "solve", "solve_dataset", "cg_begin", "cg_finish", "predict", "predict_dataset", "q_kernel", "matvec", "w_kernel", "predict_kernel")]
+     for name in ("dataset_create", "solve", "solve_dataset", "cg_begin", "cg_finish", "cg_trace", "predict", "predict_dataset", "q_kernel", "matvec", "w_kernel", "predict_kernel")]
 
 
 def _check(rc: int) -> None:
@@ -295,6 +296,23 @@ class Backend:
             _check(fn(self._h, _ptr(X), N, d, _ptr(yh), k, int(degree), gamma, coef0, cost, eps, max_iter, _ptr(alpha), _ptr(rho), _ptr(iters), _ptr(res)))
         return {"alpha": alpha, "rho": rho[0], "iterations": int(iters[0]), "delta": res[0], "delta0": res[1]}
 
+    def solve_traced(self, X, y, kernel, *, degree=3, gamma=None, coef0=0.0, cost=1.0, eps=1e-3, max_iter=None, interval=8):
+        """``solve`` through the session API, additionally returning the residual history under ``"trace"``."""
+        ds = X if isinstance(X, Dataset) else self.dataset(X)
+        max_iter = ds.N if max_iter is None else int(max_iter)
+        cg = self.cg_begin(ds, y, kernel, degree=degree, gamma=gamma, coef0=coef0, cost=cost, eps=eps)
+        done, conv = 0, False
+        while done < max_iter and not conv:
+            asked = min(interval, max_iter - done)
+            now, conv = cg.step(asked)
+            if not conv and now != done + asked:
+                raise BackendError(3, "CG session lost iterations")
+            done = now
+        tr = cg.trace()
+        res = cg.finish()
+        res["trace"] = tr
+        return res
+
     def cg_begin(self, X: "Dataset", y, kernel, *, degree=3, gamma=None, coef0=0.0, cost=1.0, eps=1e-3) -> "CGSession":
         """The same solve as a session whose iterations the caller drives (bench.py times exactly K of them)."""
         return CGSession(self, X, y, kernel, degree=degree, gamma=gamma, coef0=coef0, cost=cost, eps=eps)
@@ -392,6 +410,13 @@ class CGSession:
         done, conv = ctypes.c_uint64(), ctypes.c_int()
         _check(self.backend.lib.plssvm_b200_cg_step(self._h, int(iterations), ctypes.byref(done), ctypes.byref(conv)))
         return int(done.value), bool(conv.value)
+
+    def trace(self) -> np.ndarray:
+        """r.r after 0, 1, 2, ... completed iterations (the reference logs these per iteration, gpu_csvm.hpp:569-571)."""
+        out = np.empty(4097, dtype=self.X.dtype)
+        count = ctypes.c_size_t()
+        _check(getattr(self.backend.lib, f"plssvm_b200_cg_trace_{self.suf}")(self._h, _ptr(out), out.size, ctypes.byref(count)))
+        return out[: count.value].copy()
 
     def finish(self) -> dict:
         alpha = np.empty(self.X.N, dtype=self.X.dtype)

@@ -412,7 +412,8 @@ struct cg_session : cg_session_base {
     T cost, eps;
     std::uint32_t n;
     unsigned vblocks;
-    dbuf<T> y_d, q_full, b, x, r, dvec, Ad, part;
+    dbuf<T> y_d, q_full, b, x, r, dvec, Ad, part, trace;  // trace[k] = r.r after k iterations (k <= TRACE_CAP)
+    static constexpr std::uint64_t TRACE_CAP = 4096;
     dbuf<CGState<T>> state;
     std::unique_ptr<matvec_plan<T>> mv;
     std::uint64_t iters_enqueued = 0;
@@ -442,6 +443,7 @@ struct cg_session : cg_session_base {
         dvec.alloc(n);
         Ad.alloc(n);
         part.alloc(vblocks);
+        trace.alloc(TRACE_CAP + 1);
         state.alloc(1);
 
         PB_CUDA(cudaMemcpyAsync(y_d.p, y, N * sizeof(T), cudaMemcpyHostToDevice, st));
@@ -459,7 +461,7 @@ struct cg_session : cg_session_base {
         // r = b - Q~ x0,  delta0 = r.r,  d = r     (gpu_csvm.hpp:515-554)
         mv->run(x.p, Ad.p);
         pb::cg_residual_kernel<T><<<vblocks, pb::VEC_BLOCK, 0, st>>>(b.p, Ad.p, r.p, n, part.p, nullptr);
-        pb::cg_start_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p);
+        pb::cg_start_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p, trace.p);
         pb::cg_update_d_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += 3;
@@ -478,7 +480,7 @@ struct cg_session : cg_session_base {
         } else {
             pb::cg_update_xr_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(x.p, r.p, dvec.p, Ad.p, n, state.p, part.p);  // x += a d; r -= a Ad (588, 611-613)
         }
-        pb::cg_beta_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p, eps, nullptr);                  // delta, stop test, beta (616-625)
+        pb::cg_beta_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p, eps, iter < TRACE_CAP ? trace.p : nullptr);                  // delta, stop test, beta (616-625)
         pb::cg_update_d_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);                // d = beta d + r   (627)
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += (iter % 50 == 49) ? 6 : 5;
@@ -509,6 +511,17 @@ struct cg_session : cg_session_base {
             std::printf("[plssvm_b200] iteration %llu residuum %g (target: %g)\n", static_cast<unsigned long long>(last.iter), static_cast<double>(last.delta),
                         static_cast<double>(eps * eps * last.delta0));
         }
+    }
+
+    // residual history: out[k] = r.r after k iterations, k = 0 .. min(iterations, TRACE_CAP)
+    std::size_t get_trace(T *out, const std::size_t capacity) {
+        PB_CUDA(cudaSetDevice(ctx->device));
+        const std::size_t count = std::min<std::size_t>({ static_cast<std::size_t>(last.iter) + 1, static_cast<std::size_t>(TRACE_CAP) + 1, capacity });
+        if (count > 0) {
+            PB_CUDA(cudaMemcpyAsync(out, trace.p, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        return count;
     }
 
     // bias and the last alpha (gpu_csvm.hpp:649-653)
@@ -924,6 +937,13 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
             holder->impl = std::make_unique<cg_session<T>>(ctx, X, y, kernel, degree, gamma, coef0, cost, eps);                                                                  \
             PB_CUDA(cudaStreamSynchronize(ctx->stream));                                                                                                                         \
             *out = holder.release();                                                                                                                                             \
+        });                                                                                                                                                                      \
+    }                                                                                                                                                                            \
+    int plssvm_b200_cg_trace_##SUF(plssvm_b200_cg *cg, T *out, size_t capacity, size_t *count) {                                                                                \
+        return guarded([&] {                                                                                                                                                     \
+            PB_REQUIRE(cg != nullptr && cg->impl != nullptr && out != nullptr && count != nullptr, "cg session, out or count is NULL");                                          \
+            PB_REQUIRE(cg->impl->elem_size == static_cast<int>(sizeof(T)), "cg session has the wrong real_type");                                                                \
+            *count = static_cast<cg_session<T> *>(cg->impl.get())->get_trace(out, capacity);                                                                                     \
         });                                                                                                                                                                      \
     }                                                                                                                                                                            \
     int plssvm_b200_cg_finish_##SUF(plssvm_b200_cg *cg, T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                       \

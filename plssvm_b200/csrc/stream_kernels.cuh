@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(VEC_BLOCK) cg_residual_kernel(const T *__restr
 
 // delta0 = delta = r.r;  d = r    (gpu_csvm.hpp:545-554)
 template <typename T>
-__global__ void __launch_bounds__(VEC_BLOCK) cg_start_kernel(const T *__restrict__ part, const std::uint32_t nparts, CGState<T> *st) {
+__global__ void __launch_bounds__(VEC_BLOCK) cg_start_kernel(const T *__restrict__ part, const std::uint32_t nparts, CGState<T> *st, T *__restrict__ trace) {
     __shared__ T smem[VEC_BLOCK / 32];
     const T delta = sum_partials(part, nparts, smem);
     if (threadIdx.x == 0) {
+        if (trace != nullptr) { trace[0] = delta; }
         st->delta = delta;
         st->delta0 = delta;
         st->delta_old = delta;

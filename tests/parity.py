@@ -33,3 +33,23 @@ def check_solution(alpha, rho, want_alpha, want_rho, dtype, spread=0.0, qa_cost=
     err_rho = abs(float(rho) - float(want_rho))
     assert err_rho <= 2 * sum_tol, f"{tag}: rho error {err_rho:.3e} > {2 * sum_tol:.3e}"
     return {"alpha_rel_err": err / scale if scale > 0 else 0.0, "alpha_last_err": err_last, "rho_err": err_rho}
+
+
+def check_labels(values, ref_values, dtype, tag=""):
+    """Predicted labels must be identical to the reference's except where the reference's own decision value is within the
+    noise of zero: |f_ref| <= 10 x the largest deviation between the two value vectors, which itself must be small."""
+    values = np.asarray(values, dtype=np.float64)
+    ref_values = np.asarray(ref_values, dtype=np.float64)
+    scale = float(np.max(np.abs(ref_values)))
+    dev = float(np.max(np.abs(values - ref_values)))
+    assert dev <= (1e-4 if np.dtype(dtype) == np.float64 else 5e-2) * scale, f"{tag}: decision values deviate by {dev:.3e} (scale {scale:.3e})"
+    safe = np.abs(ref_values) > 10.0 * dev
+    mism = (np.where(values > 0, 1, -1) != np.where(ref_values > 0, 1, -1)) & safe
+    assert not mism.any(), f"{tag}: {int(mism.sum())} label mismatches outside the noise band"
+    return int(safe.sum())
+
+
+def iterations_close(got: int, ref_counts) -> bool:
+    """Within +-1 of an iteration count the reference itself produced (its own count varies run to run)."""
+    ref_counts = np.atleast_1d(ref_counts)
+    return bool(np.min(np.abs(ref_counts.astype(np.int64) - int(got))) <= 1)
