@@ -35,14 +35,16 @@ def check_solution(alpha, rho, want_alpha, want_rho, dtype, spread=0.0, qa_cost=
     return {"alpha_rel_err": err / scale if scale > 0 else 0.0, "alpha_last_err": err_last, "rho_err": err_rho}
 
 
-def check_labels(values, ref_values, dtype, tag=""):
+def check_labels(values, ref_values, dtype, spread=0.0, tag=""):
     """Predicted labels must be identical to the reference's except where the reference's own decision value is within the
-    noise of zero: |f_ref| <= 10 x the largest deviation between the two value vectors, which itself must be small."""
+    noise of zero: |f_ref| <= 10 x the largest deviation between the two value vectors, which itself must be small
+    (1e-4 fp64 / 5e-2 fp32 of the value scale, widened to 200 x the reference's own alpha spread: f sums n_sv alphas)."""
     values = np.asarray(values, dtype=np.float64)
     ref_values = np.asarray(ref_values, dtype=np.float64)
     scale = float(np.max(np.abs(ref_values)))
     dev = float(np.max(np.abs(values - ref_values)))
-    assert dev <= (1e-4 if np.dtype(dtype) == np.float64 else 5e-2) * scale, f"{tag}: decision values deviate by {dev:.3e} (scale {scale:.3e})"
+    dev_tol = max(1e-4 if np.dtype(dtype) == np.float64 else 5e-2, 200.0 * float(spread))
+    assert dev <= dev_tol * scale, f"{tag}: decision values deviate by {dev:.3e} (scale {scale:.3e}, tolerance {dev_tol:.1e})"
     safe = np.abs(ref_values) > 10.0 * dev
     mism = (np.where(values > 0, 1, -1) != np.where(ref_values > 0, 1, -1)) & safe
     assert not mism.any(), f"{tag}: {int(mism.sum())} label mismatches outside the noise band"
@@ -53,3 +55,13 @@ def iterations_close(got: int, ref_counts) -> bool:
     """Within +-1 of an iteration count the reference itself produced (its own count varies run to run)."""
     ref_counts = np.atleast_1d(ref_counts)
     return bool(np.min(np.abs(ref_counts.astype(np.int64) - int(got))) <= 1)
+
+
+def noise_dominated(trace_a, trace_b, rtol=0.1) -> bool:
+    """True if two residual histories of the SAME solve (e.g. the reference in fp32 and in fp64, or with different thread
+    counts) have already diverged by more than `rtol` before either stops: the iteration count is then decided by rounding
+    noise, not by the algorithm, and is not a meaningful parity target."""
+    m = min(len(trace_a), len(trace_b))
+    a = np.asarray(trace_a[:m], dtype=np.float64)
+    b = np.asarray(trace_b[:m], dtype=np.float64)
+    return bool(np.any(np.abs(a - b) > rtol * np.maximum(np.abs(a), np.abs(b))))
