@@ -23,7 +23,7 @@ import numpy as np
 from . import build as _build
 
 __all__ = ["Backend", "Dataset", "CGSession", "CSVM", "Parameter", "Model", "BackendError", "lib_path", "load_library",
-           "LINEAR", "POLYNOMIAL", "RBF", "kernel_id", "tile_size", "tri_num_tiles", "tri_encode", "tri_decode", "rank_range"]
+           "LINEAR", "POLYNOMIAL", "RBF", "kernel_id", "broadcast_bytes", "tile_size", "tri_num_tiles", "tri_encode", "tri_decode", "rank_range"]
 
 LINEAR, POLYNOMIAL, RBF = 0, 1, 2
 _KERNELS = {"linear": LINEAR, "polynomial": POLYNOMIAL, "poly": POLYNOMIAL, "rbf": RBF, 0: LINEAR, 1: POLYNOMIAL, 2: RBF}
@@ -147,6 +147,19 @@ def rank_range(total: int, rank: int, world_size: int):
     return int(lo.value), int(hi.value)
 
 
+def broadcast_bytes(raw: bytes, size: int, src: int = 0, device: int = 0) -> bytes:
+    """Ship `size` bytes from rank `src` to every rank of the default torch.distributed group (gloo or nccl)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.zeros(size, dtype=torch.uint8)
+    if dist.get_rank() == src:
+        t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).clone()
+    if dist.get_backend() == "nccl":
+        t = t.cuda(device)
+    dist.broadcast(t, src=src)
+    return t.cpu().numpy().tobytes()
+
+
 # ---- buffers -----------------------------------------------------------------------------------------------------------------
 def _suffix(dtype) -> str:
     dtype = np.dtype(dtype)
@@ -247,17 +260,14 @@ class Backend:
     # -- multi-GPU ------------------------------------------------------------------------------------------------------------
     def init_comm_from_torch(self) -> None:
         """One process per GPU: broadcast NCCL's unique id over the already-initialised torch.distributed group."""
-        import torch
         import torch.distributed as dist
         rank, world = dist.get_rank(), dist.get_world_size()
-        buf = (ctypes.c_char * 128)()
+        raw = b""
         if rank == 0:
+            buf = (ctypes.c_char * 128)()
             _check(self.lib.plssvm_b200_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
-        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-        if dist.get_backend() == "nccl":
-            t = t.cuda(self.device)
-        dist.broadcast(t, src=0)
-        raw = bytes(t.cpu().numpy().tobytes())
+            raw = bytes(buf.raw)
+        raw = broadcast_bytes(raw, 128, device=self.device)
         idbuf = ctypes.create_string_buffer(raw, 128)
         _check(self.lib.plssvm_b200_comm_init(self._h, rank, world, ctypes.cast(idbuf, ctypes.c_void_p)))
         self.rank, self.world_size = rank, world
