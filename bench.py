@@ -32,7 +32,10 @@ WORKLOADS = {
     "C2": (65536, 4096, "rbf", "float64", "65,536 x 4,096 dense, RBF gamma=1/d, fp64"),
     "C3": (131072, 1024, "polynomial", "float32", "131,072 x 1,024 dense, polynomial degree 3, fp32"),
     "C4": (262144, 2048, "linear", "float64", "262,144 x 2,048 dense, linear, fp64"),
+    # prediction: N = number of support vectors; test points are processed in steps of PREDICT_STEP_POINTS
+    "C5": (65536, 4096, "rbf", "float64", "predict 1,048,576 test points against a 65,536-SV RBF model (d = 4,096), fp64"),
 }
+PREDICT_STEP_POINTS = 65536
 KERNEL_IDS = {"linear": 0, "polynomial": 1, "rbf": 2}
 
 
@@ -317,10 +320,100 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ---- prediction workload (C5): run_predict_kernel throughput -----------------------------------------------------------------------
+def run_predict(args):
+    """A step = decision values of PREDICT_STEP_POINTS test points against all support vectors (2 m n_sv d FLOPs)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import plssvm_b200 as pb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    n_sv, d, kernel, dtype, desc = WORKLOADS["C5"]
+    n_sv, d = args.rows or n_sv, args.features or d
+    m = PREDICT_STEP_POINTS  # per rank and step: test points are independent units, sharded over ranks with no collective
+    F = 2.0 * m * n_sv * d
+    be = pb.Backend(local_rank)
+    SV, _ = make_device_data(n_sv, d, dtype, 47, device)
+    P, _ = make_device_data(m, d, dtype, 48 + rank, device)
+    rng = np.random.default_rng(47)
+    alpha = rng.uniform(-1, 1, n_sv)
+    alpha -= alpha.mean()
+    rho = 0.1
+    sv_ds, p_ds = be.dataset(SV), be.dataset(P)
+    for _ in range(args.warmup):
+        be.predict_values(sv_ds, alpha, rho, p_ds, kernel)
+    barrier()
+    tile_ms, launches = 0.0, 0
+    with ClockSampler(local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            vals, _ = be.predict_values(sv_ds, alpha, rho, p_ds, kernel)
+            t = be.timings()
+            tile_ms += t["matvec_tile_ms"]
+            launches += t["kernel_launches"]
+        barrier()
+        wall = time.perf_counter() - t0
+    e2e = None
+    if not args.no_e2e:
+        Ph = torch.empty((m, d), dtype=P.dtype, pin_memory=True)
+        Ph.copy_(P)
+        SVh = torch.empty((n_sv, d), dtype=P.dtype, pin_memory=True)
+        SVh.copy_(SV)
+        barrier()
+        t0 = time.perf_counter()
+        vals2, _ = be.predict_values(SVh, alpha, rho, Ph, kernel)
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        t2 = be.timings()
+        assert np.array_equal(vals, vals2)
+        e2e = {"value": world * F / t_e2e / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": t2["h2d_bytes"], "d2h_bytes_per_step": t2["d2h_bytes"], "seconds": t_e2e,
+               "points_per_s": world * m / t_e2e, "note": "one plssvm_b200_predict call: H2D of the support vectors and the points from pinned memory + norms + tiles + D2H of the values"}
+    if world > 1:
+        tt = torch.tensor([wall, tile_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        wall, tile_ms = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
+    peak = float(json.load(open(peaks_path)).get("dmma_tflops_sustained_3s", 37.0)) if os.path.exists(peaks_path) else 37.0
+    achieved = F * args.steps / (tile_ms * 1e-3) / 1e12 if tile_ms > 0 else 0.0
+    line = {
+        "metric": "predict_tflops", "value": world * F * args.steps / wall / 1e12, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C5: {desc}", "points_per_step_per_gpu": m, "support_vectors": n_sv, "features": d, "flops_per_step_per_gpu": F,
+                   "l2": "points (2.1 GB) and support vectors (2.1 GB) larger than L2"},
+        "points_per_s": world * m * args.steps / wall, "seconds_for_1048576_points": 1048576.0 / (world * m * args.steps / wall),
+        "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": "tile_kernel_dmma<rbf, rect>"},
+        "cpu_baseline": None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "C5":
+        run_predict(args)
     else:
         run_ours(args)
 
