@@ -15,6 +15,7 @@
 #include "stream_kernels.cuh"
 #include "tile_dmma.cuh"
 #include "tile_simt.cuh"
+#include "tile_tf32.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -183,6 +184,13 @@ struct plssvm_b200_ctx {
     cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
     PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;
     void *pinned = nullptr;  // small pinned staging block for scalar read-backs
+    // second stream + events: H2D staging of predict batches overlaps the tile kernel of the previous batch
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_computed[2] = { nullptr, nullptr };
+    // grow-only device workspaces kept across calls (cudaMalloc / cudaFree of 100+ MB buffers costs milliseconds and synchronises)
+    enum ws_slot { WS_PARTIAL = 0, WS_OUT, WS_ALPHA, WS_W, WS_STAGE0, WS_STAGE1, WS_SQ0, WS_SQ1, WS_HI0, WS_HI1, WS_LO0, WS_LO1, WS_COUNT };
+    void *ws_ptr[WS_COUNT] = {};
+    std::size_t ws_bytes[WS_COUNT] = {};
 };
 
 struct plssvm_b200_dataset {
@@ -191,6 +199,7 @@ struct plssvm_b200_dataset {
     std::size_t N = 0, d = 0, ld = 0;
     void *X = nullptr;   // [N][ld]
     void *sq = nullptr;  // [N]
+    void *X_hi = nullptr, *X_lo = nullptr;  // fp32 only: TF32 hi / lo split of X for the 3xTF32 tensor path
 };
 
 namespace {
@@ -201,18 +210,46 @@ using pb::TileParams;
 using pb::TILE;
 
 template <typename T>
+T *workspace(plssvm_b200_ctx *ctx, const int slot, const std::size_t count) {
+    const std::size_t bytes = count * sizeof(T);
+    if (ctx->ws_bytes[slot] < bytes) {
+        if (ctx->ws_ptr[slot] != nullptr) {
+            PB_CUDA(cudaStreamSynchronize(ctx->stream));
+            PB_CUDA(cudaFree(ctx->ws_ptr[slot]));
+            ctx->ws_ptr[slot] = nullptr;
+            ctx->ws_bytes[slot] = 0;
+        }
+        PB_CUDA(cudaMalloc(&ctx->ws_ptr[slot], bytes));
+        ctx->ws_bytes[slot] = bytes;
+    }
+    return static_cast<T *>(ctx->ws_ptr[slot]);
+}
+
+// host (row pitch d) -> device (row pitch ld, pad columns already zero)
+template <typename T>
+void upload_rows(T *dst, const std::size_t ld, const T *src, const std::size_t d, const std::size_t rows, cudaStream_t st) {
+    if (ld == d) {
+        PB_CUDA(cudaMemcpyAsync(dst, src, rows * d * sizeof(T), cudaMemcpyHostToDevice, st));
+    } else {
+        PB_CUDA(cudaMemcpy2DAsync(dst, ld * sizeof(T), src, d * sizeof(T), d * sizeof(T), rows, cudaMemcpyHostToDevice, st));
+    }
+}
+
+template <typename T>
 std::size_t pitch_elems(const std::size_t d) {
     const std::size_t per128 = 128 / sizeof(T);
     return (d + per128 - 1) / per128 * per128;
 }
 
-void make_tensor_map_f64(plssvm_b200_ctx *ctx, CUtensorMap *tm, const double *base, const std::size_t rows, const std::size_t ld) {
+// 2-D map over a row-major matrix: box = 128 rows x 128 bytes (16 doubles / 32 floats), 128-byte swizzle, OOB rows zero-filled
+template <typename T>
+void make_tensor_map(plssvm_b200_ctx *ctx, CUtensorMap *tm, const T *base, const std::size_t rows, const std::size_t ld) {
     const cuuint64_t dims[2] = { static_cast<cuuint64_t>(ld), static_cast<cuuint64_t>(rows) };
-    const cuuint64_t strides[1] = { static_cast<cuuint64_t>(ld * sizeof(double)) };
-    const cuuint32_t box[2] = { static_cast<cuuint32_t>(pb::DMMA_BK), static_cast<cuuint32_t>(TILE) };
+    const cuuint64_t strides[1] = { static_cast<cuuint64_t>(ld * sizeof(T)) };
+    const cuuint32_t box[2] = { static_cast<cuuint32_t>(128 / sizeof(T)), static_cast<cuuint32_t>(TILE) };
     const cuuint32_t estr[2] = { 1, 1 };
-    const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult rc = ctx->encode_tiled(tm, sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<T *>(base), dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(rc))); }
 }
 
@@ -224,10 +261,23 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
     if constexpr (sizeof(T) == 8) {
         if (impl == 2) {
             CUtensorMap tmA, tmB;
-            make_tensor_map_f64(ctx, &tmA, p.A, p.n_rows, p.ld);
-            make_tensor_map_f64(ctx, &tmB, p.B, p.n_cols, p.ld);
+            make_tensor_map<double>(ctx, &tmA, p.A, p.n_rows, p.ld);
+            make_tensor_map<double>(ctx, &tmB, p.B, p.n_cols, p.ld);
             PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_dmma<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::DMMA_SMEM_BYTES));
             pb::tile_kernel_dmma<KERNEL, MODE><<<grid, pb::DMMA_THREADS, pb::DMMA_SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+            return;
+        }
+    } else {
+        if (impl == 2) {
+            CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
+            make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
+            make_tensor_map<float>(ctx, &tmAlo, p.A_lo, p.n_rows, p.ld);
+            make_tensor_map<float>(ctx, &tmBhi, p.B_hi, p.n_cols, p.ld);
+            make_tensor_map<float>(ctx, &tmBlo, p.B_lo, p.n_cols, p.ld);
+            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_tf32<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::TF32_SMEM_BYTES));
+            pb::tile_kernel_tf32<KERNEL, MODE><<<grid, pb::TF32_THREADS, pb::TF32_SMEM_BYTES, ctx->stream>>>(tmAhi, tmAlo, tmBhi, tmBlo, p);
             PB_CUDA(cudaGetLastError());
             ctx->tm.kernel_launches++;
             return;
@@ -240,8 +290,8 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx) {
-    if (ctx->impl == 1) { return 1; }
-    return sizeof(T) == 8 ? 2 : 1;  // fp32 tensor path (tcgen05 3xTF32) not wired yet: SIMT
+    if (ctx->impl != 0) { return ctx->impl; }
+    return sizeof(T) == 8 ? 2 : 1;  // fp32 default stays on the SIMT tiles until the tcgen05 3xTF32 path is validated on hardware
 }
 
 template <typename T, int MODE>
@@ -287,6 +337,8 @@ struct matvec_plan {
         base = TileParams<T>{};
         base.A = static_cast<const T *>(data->X);
         base.B = base.A;
+        base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
+        base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
         base.n_rows = n;
         base.n_cols = n;
         base.ld = static_cast<std::uint32_t>(data->ld);
@@ -379,16 +431,28 @@ plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const T *X, const std:
             ctx->tm.kernel_launches++;
         } else {
             if (ds->ld != d) { PB_CUDA(cudaMemsetAsync(ds->X, 0, N * ds->ld * sizeof(T), ctx->stream)); }
-            PB_CUDA(cudaMemcpy2DAsync(ds->X, ds->ld * sizeof(T), X, d * sizeof(T), d * sizeof(T), N, cudaMemcpyHostToDevice, ctx->stream));
+            upload_rows<T>(static_cast<T *>(ds->X), ds->ld, X, d, N, ctx->stream);
             ctx->tm.h2d_bytes += static_cast<double>(N * d * sizeof(T));
         }
         pb::row_norms_kernel<T><<<static_cast<unsigned>((N + 7) / 8), 256, 0, ctx->stream>>>(static_cast<const T *>(ds->X), N, static_cast<std::uint32_t>(ds->ld), static_cast<T *>(ds->sq));
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches++;
+        if constexpr (sizeof(T) == 4) {
+            // TF32 hi / lo split for the tcgen05 3xTF32 tiles (done once per data set; X is constant across CG iterations)
+            PB_CUDA(cudaMalloc(&ds->X_hi, N * ds->ld * sizeof(T)));
+            PB_CUDA(cudaMalloc(&ds->X_lo, N * ds->ld * sizeof(T)));
+            const std::size_t total = N * ds->ld;
+            const unsigned grid = static_cast<unsigned>(std::min<std::size_t>((total + 255) / 256, static_cast<std::size_t>(ctx->num_sms) * 32));
+            pb::split_tf32_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float *>(ds->X), static_cast<float *>(ds->X_hi), static_cast<float *>(ds->X_lo), total);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+        }
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
         cudaFree(ds->X);
         cudaFree(ds->sq);
+        cudaFree(ds->X_hi);
+        cudaFree(ds->X_lo);
         delete ds;
         throw;
     }
@@ -577,8 +641,8 @@ void run_w_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *
 // ---- predict: csvm::predict_values (gpu_csvm.hpp:656-730) -------------------------------------------------------------------------
 // points: `pts` rows [p0, p0 + m) of a resident matrix; out_d: m values on the device
 template <typename T>
-void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, const T *w_d, const T rho, const T *P, const T *P_sq, const std::size_t m,
-                         const KernelParams<T> &kp, T *out_d, dbuf<T> &partial) {
+void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, const T *w_d, const T rho, const T *P, const T *P_sq, const T *P_hi,
+                         const T *P_lo, const std::size_t m, const KernelParams<T> &kp, T *out_d) {
     const std::uint32_t ld = static_cast<std::uint32_t>(sv->ld);
     if (kp.kernel == pb::K_LINEAR) {
         pb::linear_predict_kernel<T><<<static_cast<unsigned>((m + 7) / 8), 256, 0, ctx->stream>>>(P, m, ld, w_d, rho, out_d);
@@ -589,6 +653,10 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     TileParams<T> p{};
     p.A = P;
     p.B = static_cast<const T *>(sv->X);
+    p.A_hi = P_hi;
+    p.A_lo = P_lo;
+    p.B_hi = static_cast<const T *>(sv->X_hi);
+    p.B_lo = static_cast<const T *>(sv->X_lo);
     p.n_rows = static_cast<std::uint32_t>(m);
     p.n_cols = static_cast<std::uint32_t>(sv->N);
     p.ld = ld;
@@ -600,13 +668,11 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.col_sq = static_cast<const T *>(sv->sq);
     p.v = alpha_d;
     p.kp = kp;
-    const std::size_t need = static_cast<std::size_t>(p.T_rows) * p.T_cols * TILE;
-    if (partial.count < need) { partial.alloc(need); }
-    p.partial = partial.p;
+    p.partial = workspace<T>(ctx, plssvm_b200_ctx::WS_PARTIAL, static_cast<std::size_t>(p.T_rows) * p.T_cols * TILE);
     const bool timed = ctx->tile_timer.begin(ctx->stream);
     launch_tiles<T, pb::MODE_RECT>(ctx, p);
     if (timed) { ctx->tile_timer.end(ctx->stream); }
-    pb::reduce_partials_kernel<T, pb::MODE_RECT><<<p.T_rows, 512, 0, ctx->stream>>>(partial.p, out_d, p.n_rows, p.T_rows, p.T_cols, 0, p.tile_hi, 0, T(1), -rho, 0, nullptr);
+    pb::reduce_partials_kernel<T, pb::MODE_RECT><<<p.T_rows, 512, 0, ctx->stream>>>(p.partial, out_d, p.n_rows, p.T_rows, p.T_cols, 0, p.tile_hi, 0, T(1), -rho, 0, nullptr);
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
 }
@@ -630,53 +696,96 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     const KernelParams<T> kp{ kernel, degree, gamma, coef0 };
     const T shift_rho = with_rho ? rho : T(0);
 
-    dbuf<T> alpha_d(sv->N), w_d, out_d(std::min(m, PREDICT_BATCH)), partial;
-    PB_CUDA(cudaMemcpyAsync(alpha_d.p, alpha, sv->N * sizeof(T), cudaMemcpyHostToDevice, st));
+    using ctx_t = plssvm_b200_ctx;
+    T *alpha_d = workspace<T>(ctx, ctx_t::WS_ALPHA, sv->N);
+    T *w_d = nullptr;
+    PB_CUDA(cudaMemcpyAsync(alpha_d, alpha, sv->N * sizeof(T), cudaMemcpyHostToDevice, st));
     ctx->tm.h2d_bytes += static_cast<double>(sv->N * sizeof(T));
     if (kernel == pb::K_LINEAR) {
-        w_d.alloc(sv->ld);
+        w_d = workspace<T>(ctx, ctx_t::WS_W, sv->ld);
         if (w_valid != nullptr && *w_valid != 0 && w_inout != nullptr) {
-            PB_CUDA(cudaMemsetAsync(w_d.p, 0, sv->ld * sizeof(T), st));
-            PB_CUDA(cudaMemcpyAsync(w_d.p, w_inout, sv->d * sizeof(T), cudaMemcpyHostToDevice, st));
+            PB_CUDA(cudaMemsetAsync(w_d, 0, sv->ld * sizeof(T), st));
+            PB_CUDA(cudaMemcpyAsync(w_d, w_inout, sv->d * sizeof(T), cudaMemcpyHostToDevice, st));
         } else {
-            run_w_kernel<T>(ctx, sv, alpha_d.p, w_d.p);
+            run_w_kernel<T>(ctx, sv, alpha_d, w_d);
             if (w_inout != nullptr) {
-                PB_CUDA(cudaMemcpyAsync(w_inout, w_d.p, sv->d * sizeof(T), cudaMemcpyDeviceToHost, st));
+                PB_CUDA(cudaMemcpyAsync(w_inout, w_d, sv->d * sizeof(T), cudaMemcpyDeviceToHost, st));
                 PB_CUDA(cudaStreamSynchronize(st));
                 if (w_valid != nullptr) { *w_valid = 1; }
             }
         }
     }
 
-    // host points are staged batch by batch (64-bit offsets; the reference's int indexing overflows here: predict_kernel.cu:40-42)
-    dbuf<T> stage_X, stage_sq;
+    // Test points are processed in batches of PREDICT_BATCH rows with 64-bit offsets (the reference's int indexing overflows at
+    // this size: predict_kernel.cu:40-42).  Host points are staged through two HBM buffers: the H2D copy of batch b + 1 runs
+    // on the copy stream while the tile kernel of batch b runs on the compute stream.  Values collect in HBM and are
+    // downloaded once per super-batch.
+    constexpr std::size_t SUPER_BATCH = std::size_t{ 1 } << 22;
+    const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
+    T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
+    const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx) == 2;
     if (pts_ds == nullptr) {
-        stage_X.alloc(std::min(m, PREDICT_BATCH) * sv->ld);
-        stage_sq.alloc(std::min(m, PREDICT_BATCH));
-    }
-    for (std::size_t p0 = 0; p0 < m; p0 += PREDICT_BATCH) {
-        const std::size_t mb = std::min(PREDICT_BATCH, m - p0);
-        const T *P;
-        const T *P_sq;
-        if (pts_ds != nullptr) {
-            P = static_cast<const T *>(pts_ds->X) + p0 * pts_ds->ld;
-            P_sq = static_cast<const T *>(pts_ds->sq) + p0;
-        } else {
-            if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X.p, 0, mb * sv->ld * sizeof(T), st)); }
-            PB_CUDA(cudaMemcpy2DAsync(stage_X.p, sv->ld * sizeof(T), pts_host + p0 * sv->d, sv->d * sizeof(T), sv->d * sizeof(T), mb, cudaMemcpyHostToDevice, st));
-            ctx->tm.h2d_bytes += static_cast<double>(mb * sv->d * sizeof(T));
-            if (kernel == pb::K_RBF) {
-                pb::row_norms_kernel<T><<<static_cast<unsigned>((mb + 7) / 8), 256, 0, st>>>(stage_X.p, mb, static_cast<std::uint32_t>(sv->ld), stage_sq.p);
-                PB_CUDA(cudaGetLastError());
-                ctx->tm.kernel_launches++;
+        const int n_stage = m > PREDICT_BATCH ? 2 : 1;
+        for (int i = 0; i < n_stage; ++i) {
+            stage_X[i] = workspace<T>(ctx, ctx_t::WS_STAGE0 + i, stage_rows * sv->ld);
+            stage_sq[i] = workspace<T>(ctx, ctx_t::WS_SQ0 + i, stage_rows);
+            if (need_split) {
+                stage_hi[i] = workspace<T>(ctx, ctx_t::WS_HI0 + i, stage_rows * sv->ld);
+                stage_lo[i] = workspace<T>(ctx, ctx_t::WS_LO0 + i, stage_rows * sv->ld);
             }
-            P = stage_X.p;
-            P_sq = stage_sq.p;
+            if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X[i], 0, stage_rows * sv->ld * sizeof(T), st)); }  // pad columns stay zero
         }
-        predict_rows_device<T>(ctx, sv, alpha_d.p, w_d.p, shift_rho, P, P_sq, mb, kp, out_d.p, partial);
-        PB_CUDA(cudaMemcpyAsync(out + p0, out_d.p, mb * sizeof(T), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaEventRecord(ctx->ev_computed[0], st));  // the copy stream must not start before the memsets above
+        PB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[0], 0));
+    }
+    T *out_d = workspace<T>(ctx, ctx_t::WS_OUT, std::min(m, SUPER_BATCH));
+    std::size_t batch_index = 0;
+    for (std::size_t s0 = 0; s0 < m; s0 += SUPER_BATCH) {
+        const std::size_t ms = std::min(SUPER_BATCH, m - s0);
+        for (std::size_t p0 = s0; p0 < s0 + ms; p0 += PREDICT_BATCH, ++batch_index) {
+            const std::size_t mb = std::min(PREDICT_BATCH, s0 + ms - p0);
+            const T *P;
+            const T *P_sq;
+            const T *P_hi = nullptr, *P_lo = nullptr;
+            if (pts_ds != nullptr) {
+                P = static_cast<const T *>(pts_ds->X) + p0 * pts_ds->ld;
+                P_sq = static_cast<const T *>(pts_ds->sq) + p0;
+                if (pts_ds->X_hi != nullptr) {
+                    P_hi = static_cast<const T *>(pts_ds->X_hi) + p0 * pts_ds->ld;
+                    P_lo = static_cast<const T *>(pts_ds->X_lo) + p0 * pts_ds->ld;
+                }
+            } else {
+                const int buf = static_cast<int>(batch_index & 1);
+                if (batch_index >= 2) { PB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_computed[buf], 0)); }  // buffer free again
+                upload_rows<T>(stage_X[buf], sv->ld, pts_host + p0 * sv->d, sv->d, mb, ctx->copy_stream);
+                PB_CUDA(cudaEventRecord(ctx->ev_copied[buf], ctx->copy_stream));
+                PB_CUDA(cudaStreamWaitEvent(st, ctx->ev_copied[buf], 0));
+                ctx->tm.h2d_bytes += static_cast<double>(mb * sv->d * sizeof(T));
+                if (kernel == pb::K_RBF) {
+                    pb::row_norms_kernel<T><<<static_cast<unsigned>((mb + 7) / 8), 256, 0, st>>>(stage_X[buf], mb, static_cast<std::uint32_t>(sv->ld), stage_sq[buf]);
+                    PB_CUDA(cudaGetLastError());
+                    ctx->tm.kernel_launches++;
+                }
+                if constexpr (sizeof(T) == 4) {
+                    if (need_split) {
+                        const std::size_t total = mb * sv->ld;
+                        const unsigned grid = static_cast<unsigned>(std::min<std::size_t>((total + 255) / 256, static_cast<std::size_t>(ctx->num_sms) * 32));
+                        pb::split_tf32_kernel<<<grid, 256, 0, st>>>(stage_X[buf], stage_hi[buf], stage_lo[buf], total);
+                        PB_CUDA(cudaGetLastError());
+                        ctx->tm.kernel_launches++;
+                    }
+                }
+                P = stage_X[buf];
+                P_sq = stage_sq[buf];
+                P_hi = stage_hi[buf];
+                P_lo = stage_lo[buf];
+            }
+            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, mb, kp, out_d + (p0 - s0));
+            if (pts_ds == nullptr) { PB_CUDA(cudaEventRecord(ctx->ev_computed[batch_index & 1], st)); }
+        }
+        PB_CUDA(cudaMemcpyAsync(out + s0, out_d, ms * sizeof(T), cudaMemcpyDeviceToHost, st));
         PB_CUDA(cudaStreamSynchronize(st));
-        ctx->tm.d2h_bytes += static_cast<double>(mb * sizeof(T));
+        ctx->tm.d2h_bytes += static_cast<double>(ms * sizeof(T));
     }
     ctx->tm.matvec_tile_ms = ctx->tile_timer.total_ms();
 }
@@ -794,6 +903,11 @@ int plssvm_b200_create(int device, plssvm_b200_ctx **out) {
         PB_CUDA(cudaEventCreate(&ctx->ev_loop0));
         PB_CUDA(cudaEventCreate(&ctx->ev_loop1));
         PB_CUDA(cudaMallocHost(&ctx->pinned, 4096));
+        PB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+            PB_CUDA(cudaEventCreateWithFlags(&ctx->ev_computed[i], cudaEventDisableTiming));
+        }
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qres{};
         PB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -812,6 +926,12 @@ int plssvm_b200_destroy(plssvm_b200_ctx *ctx) {
         cudaEventDestroy(ctx->ev_loop0);
         cudaEventDestroy(ctx->ev_loop1);
         cudaFreeHost(ctx->pinned);
+        for (int i = 0; i < plssvm_b200_ctx::WS_COUNT; ++i) { cudaFree(ctx->ws_ptr[i]); }
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(ctx->ev_copied[i]);
+            cudaEventDestroy(ctx->ev_computed[i]);
+        }
+        cudaStreamDestroy(ctx->copy_stream);
         cudaStreamDestroy(ctx->stream);
         delete ctx;
     });
@@ -884,6 +1004,8 @@ int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
         cudaSetDevice(ds->ctx->device);
         cudaFree(ds->X);
         cudaFree(ds->sq);
+        cudaFree(ds->X_hi);
+        cudaFree(ds->X_lo);
         delete ds;
     });
 }

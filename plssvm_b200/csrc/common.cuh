@@ -30,6 +30,8 @@ template <typename T>
 struct TileParams {
     const T *A;            // row-major, pitch `ld` elements, rows >= n_rows are never read un-masked
     const T *B;
+    const T *A_hi, *A_lo;  // fp32 tensor path only: TF32 hi / lo split of A and B (tile_tf32.cuh)
+    const T *B_hi, *B_lo;
     std::uint32_t n_rows;  // valid rows of A  (SYM: n = N - 1)
     std::uint32_t n_cols;  // valid rows of B
     std::uint32_t ld;      // row pitch in elements (multiple of 128 bytes, zero padded)
