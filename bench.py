@@ -284,11 +284,14 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (the tile kernel) ---------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
     peak, peak_src = 37.0, "vendor figure (fallback: profiles/peaks_b200.json missing)"
-    key = "dmma_tflops_sustained_3s" if dtype == "float64" else "ffma_tflops"
+    tensor = t_after["impl_used"] == 2
+    key = "dmma_tflops_sustained_3s" if dtype == "float64" else ("cublas_sgemm_tf32_tflops_sustained_3s" if tensor else "ffma_tflops")
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
         if key in pk:
             peak, peak_src = float(pk[key]), f"measured on this pool's B200 by tools/peak_probe ({key}; profiles/peaks_b200.json)"
+            if dtype != "float64" and tensor:  # 3xTF32: three TF32 MMAs per algorithmic fp32 product
+                peak, peak_src = peak / 3.0, peak_src + " / 3 (3xTF32 split)"
     avg_tile_s = tile_ms / max(tile_calls, 1) * 1e-3
     achieved = (F / world) / avg_tile_s / 1e12 if avg_tile_s > 0 else 0.0
     traffic = None
@@ -296,7 +299,7 @@ def run_ours(args):
     if os.path.exists(ncu_path):
         traffic = json.load(open(ncu_path)).get(args.workload)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "tile_kernel_dmma<rbf, sym>" if t_after["impl_used"] == 2 else "tile_kernel_simt", "peak_source": peak_src,
+                "kernel": ("tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)") + f"<{kernel}, sym>" if tensor else "tile_kernel_simt", "peak_source": peak_src,
                 "avg_launch_ms": avg_tile_s * 1e3, "launches_timed": int(tile_calls), "flops_per_launch": F / world}
 
     cpu_baseline = None

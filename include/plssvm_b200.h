@@ -52,7 +52,7 @@ typedef struct plssvm_b200_timings {
     double matvec_flops;      /* algorithmic FLOPs of ONE matvec: d * n * (n + 1)   */
     double h2d_bytes;
     double d2h_bytes;
-    int impl_used;            /* 1 = SIMT FMA tiles, 2 = tensor-core tiles (fp64: TMA + DMMA) */
+    int impl_used;            /* 1 = SIMT FMA tiles, 2 = tensor-core tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32) */
     int reserved;
 } plssvm_b200_timings;
 

@@ -291,7 +291,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx) {
     if (ctx->impl != 0) { return ctx->impl; }
-    return sizeof(T) == 8 ? 2 : 1;  // fp32 default stays on the SIMT tiles until the tcgen05 3xTF32 path is validated on hardware
+    return 2;  // tensor-core tiles: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
 }
 
 template <typename T, int MODE>
