@@ -1,0 +1,175 @@
+"""Full-size parity checks at BASELINE.json's shapes (run with ``-m gpu``).
+
+The CPU oracle needs ~25 minutes for ONE matvec at C2 and hours at C4, so at full size the implicit matvec is
+checked through properties that do not need the whole product on the CPU:
+
+* row-sampled check: for a random sample S of output rows, (Q~ v)_S is recomputed from the definition
+  Q~_ij = k(x_i, x_j) + QA_cost - q_i - q_j + delta_ij / C  (a) with torch fp64 GEMMs on the GPU (an independent
+  implementation: cuBLAS) for 256 rows and (b) with the CPU oracle's own kernel function for 3 rows;
+* the q-vector against the oracle on sampled rows;
+* symmetry u.(Q~ v) = v.(Q~ u) and linearity on the full vectors;
+* C1 (the reference's own CPU-runnable configuration) is solved end to end against the oracle;
+* C5: decision values of sampled test points against the oracle's predict.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+import plssvm_b200 as pb
+from parity import check_labels, check_solution, iterations_close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from bench import KERNEL_IDS, WORKLOADS, make_device_data  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def be():
+    b = pb.Backend(0)
+    yield b
+    b.close()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return oracle.Oracle("reference" if oracle.available("reference") else "port")
+
+
+def _kernel_rows_torch(X, rows, kernel, gamma, degree=3, coef0=0.0):
+    """k(x_i, x_j) for i in rows, all j < n, by torch fp64 (cuBLAS) — independent of the library under test."""
+    import torch
+    A = X[rows].double()
+    n = X.shape[0] - 1
+    G = A @ X[:n].double().T
+    if kernel == "linear":
+        return G
+    if kernel == "polynomial":
+        return (gamma * G + coef0) ** degree
+    sq = (X[:n].double() ** 2).sum(1)
+    d2 = (sq[rows][:, None] + sq[None, :] - 2 * G).clamp_min(0)
+    return torch.exp(-gamma * d2)
+
+
+@pytest.mark.parametrize("workload", ["C2", "C3", "C4"])
+def test_full_size_matvec_row_sampled(be, orc, workload):
+    import torch
+    N, d, kernel, dtype, _ = WORKLOADS[workload]
+    dev = torch.device("cuda", 0)
+    X, y = make_device_data(N, d, dtype, 42 + list(WORKLOADS).index(workload), dev)
+    n = N - 1
+    gamma, cost = 1.0 / d, 1.0
+    ds = be.dataset(X)
+    q, k_last = be.run_q_kernel(ds, kernel, gamma=gamma)
+    qa = float(k_last) + 1.0 / cost
+    rng = np.random.default_rng(11)
+    npdt = np.dtype(dtype)
+    u = rng.standard_normal(n).astype(npdt)
+    v = rng.uniform(1.0, 2.0, n).astype(npdt)
+    z = np.zeros(n, npdt)
+    Qv = be.run_svm_kernel(ds, q, v, z, qa, 1.0 / cost, 1.0, kernel, gamma=gamma)
+    t = be.timings()
+    assert t["impl_used"] == 2 and t["matvec_calls"] == 1
+
+    tol = 1e-11 if npdt == np.float64 else 2e-4
+    # (a) 256 sampled rows, torch fp64 reference
+    rows = torch.from_numpy(np.sort(rng.choice(n, 256, replace=False))).to(dev)
+    K = _kernel_rows_torch(X, rows, kernel, gamma)
+    q_t = torch.from_numpy(q.astype(np.float64)).to(dev)
+    v_t = torch.from_numpy(v.astype(np.float64)).to(dev)
+    Qrows = K + qa - q_t[rows][:, None] - q_t[None, :]
+    want = Qrows @ v_t + v_t[rows] / cost
+    got = torch.from_numpy(Qv.astype(np.float64)).to(dev)[rows]
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) <= tol * scale
+    # q itself on the sampled rows (rbf q uses the direct squared distance; the reference value is k(x_i, x_N))
+    A, xN = X[rows].double(), X[n].double()
+    if kernel == "rbf":
+        kq = torch.exp(-gamma * ((A - xN[None, :]) ** 2).sum(1))
+    else:
+        kq = A @ xN if kernel == "linear" else (gamma * (A @ xN)) ** 3
+    assert float((q_t[rows] - kq).abs().max()) <= tol * max(1.0, float(kq.abs().max()))
+
+    # (b) 3 rows with the CPU oracle's own kernel function (sequential FMA semantics)
+    Xh_rows = {int(r): X[int(r)].cpu().numpy() for r in rows[:3].cpu().numpy()}
+    sample_cols = rng.choice(n, 4096, replace=False)
+    Xh_cols = X[torch.from_numpy(sample_cols).to(dev)].cpu().numpy()
+    x_last = X[n].cpu().numpy()
+    for r, xr in Xh_rows.items():
+        kr = np.array([orc.kernel_function(KERNEL_IDS[kernel], xr, xc, gamma=gamma) for xc in Xh_cols])
+        Kr_t = K[(rows == r).nonzero()[0, 0]][torch.from_numpy(sample_cols).to(dev)].cpu().numpy()
+        assert np.max(np.abs(kr - Kr_t)) <= tol * max(1.0, np.max(np.abs(kr)))
+        assert abs(orc.kernel_function(KERNEL_IDS[kernel], xr, x_last, gamma=gamma) - q[r]) <= tol * max(1.0, abs(q[r]))
+
+    # symmetry and linearity on the full vectors
+    Qu = be.run_svm_kernel(ds, q, u, z, qa, 1.0 / cost, 1.0, kernel, gamma=gamma)
+    ptol = 1e-10 if npdt == np.float64 else 5e-3
+    uQv, vQu = float(np.dot(u.astype(np.float64), Qv.astype(np.float64))), float(np.dot(v.astype(np.float64), Qu.astype(np.float64)))
+    assert abs(uQv - vQu) <= ptol * np.linalg.norm(u.astype(np.float64)) * np.linalg.norm(Qv.astype(np.float64))
+    w = (2 * u - 3 * v).astype(npdt)
+    Qw = be.run_svm_kernel(ds, q, w, z, qa, 1.0 / cost, 1.0, kernel, gamma=gamma).astype(np.float64)
+    lin = 2 * Qu.astype(np.float64) - 3 * Qv.astype(np.float64)
+    assert np.max(np.abs(Qw - lin)) <= ptol * np.max(np.abs(lin))
+    # add = -1 and an initial ret: ret += add * Q~ v
+    ret = be.run_svm_kernel(ds, q, v, u, qa, 1.0 / cost, -1.0, kernel, gamma=gamma).astype(np.float64)
+    assert np.max(np.abs(ret - (u.astype(np.float64) - Qv.astype(np.float64)))) <= ptol * np.max(np.abs(Qv))
+    del ds, X
+    torch.cuda.empty_cache()
+
+
+def test_config1_end_to_end_against_the_oracle(be, orc):
+    """C1 = 5,000 x 1,000 linear fp64 eps 1e-8: the reference's own CPU-runnable configuration, full fit + predict."""
+    import torch
+    N, d, kernel, dtype, _ = WORKLOADS["C1"]
+    X, y = make_device_data(N, d, dtype, 42, torch.device("cuda", 0))
+    Xh, yh = X.cpu().numpy(), y.cpu().numpy()
+    r = be.solve_traced(Xh, yh, kernel, eps=1e-8)
+    ref = orc.solve(0, Xh, yh, gamma=1.0 / d, eps=1e-8, trace=True)
+    orc.set_threads(max(1, orc.max_threads() // 2))  # a second run with another thread count measures the reference's own spread
+    ref2 = orc.solve(0, Xh, yh, gamma=1.0 / d, eps=1e-8)
+    orc.set_threads(orc.max_threads())
+    assert iterations_close(r["iterations"], [ref["iterations"], ref2["iterations"]]), (r["iterations"], ref["iterations"], ref2["iterations"])
+    assert np.allclose(r["trace"][:3], ref["trace"][:3], rtol=1e-8)
+    spread = float(np.max(np.abs(ref["alpha"] - ref2["alpha"])) / np.max(np.abs(ref["alpha"]))) if ref["iterations"] == ref2["iterations"] else 1e-3
+    if r["iterations"] == ref["iterations"]:
+        check_solution(r["alpha"], r["rho"], ref["alpha"], ref["rho"], np.float64, spread=spread, qa_cost=float(np.dot(Xh[-1], Xh[-1])) + 1.0, tag="C1")
+    P, _ = make_device_data(2000, d, dtype, 77, torch.device("cuda", 0))
+    Ph = P.cpu().numpy()
+    vals, w = be.predict_values(Xh, r["alpha"], r["rho"], Ph, kernel)
+    ref_vals, ref_w = orc.predict(0, Xh, ref["alpha"], ref["rho"], Ph, gamma=1.0 / d)
+    if r["iterations"] == ref["iterations"]:
+        check_labels(vals, ref_vals, np.float64, spread=spread, tag="C1")
+    same_model, _ = orc.predict(0, Xh, r["alpha"], r["rho"], Ph, gamma=1.0 / d)
+    assert np.max(np.abs(vals - same_model)) <= 1e-11 * np.max(np.abs(same_model))
+    assert (np.where(vals > 0, 1, -1) == np.where(same_model > 0, 1, -1)).all()  # identical labels for the identical model
+
+
+def test_config5_predict_sampled_against_the_oracle(be, orc):
+    """C5 shape: 65,536 support vectors, d = 4,096, rbf; one full 65,536-point step on the GPU, 24 sampled points on the oracle."""
+    import torch
+    n_sv, d, kernel, dtype, _ = WORKLOADS["C5"]
+    dev = torch.device("cuda", 0)
+    SV, _ = make_device_data(n_sv, d, dtype, 47, dev)
+    P, _ = make_device_data(65536, d, dtype, 48, dev)
+    rng = np.random.default_rng(47)
+    alpha = rng.uniform(-1, 1, n_sv)
+    alpha -= alpha.mean()
+    rho = 0.1
+    sv_ds, p_ds = be.dataset(SV), be.dataset(P)
+    vals, _ = be.predict_values(sv_ds, alpha, rho, p_ds, kernel)
+    idx = np.sort(rng.choice(65536, 24, replace=False))
+    ref, _ = orc.predict(2, SV.cpu().numpy(), alpha, rho, P[torch.from_numpy(idx).to(dev)].cpu().numpy(), gamma=1.0 / d)
+    assert np.max(np.abs(vals[idx] - ref)) <= 1e-11 * max(1.0, np.max(np.abs(ref)))
+    # all points against torch fp64 (cuBLAS) in chunks
+    sq_sv = (SV ** 2).sum(1)
+    a_t = torch.from_numpy(alpha).to(dev)
+    for c0 in range(0, 65536, 16384):
+        Pc = P[c0:c0 + 16384]
+        d2 = ((Pc ** 2).sum(1)[:, None] + sq_sv[None, :] - 2 * (Pc @ SV.T)).clamp_min(0)
+        want = (torch.exp(-d2 / d) @ a_t - rho).cpu().numpy()
+        assert np.max(np.abs(vals[c0:c0 + 16384] - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
+        assert (np.where(vals[c0:c0 + 16384] > 0, 1, -1) == np.where(want > 0, 1, -1))[np.abs(want) > 1e-9].all()
