@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=0, help="override the number of data points (development only; marks the line as non-headline)")
     ap.add_argument("--features", type=int, default=0, help="override the number of features (development only)")
     ap.add_argument("--tile-impl", type=int, default=0, help="0 auto, 1 SIMT tiles, 2 tensor-core tiles")
+    ap.add_argument("--linear-factorized", action="store_true", help="linear kernel only: time the factorised X (X^T v) matvec (HBM-bound) instead of the implicit tiles")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
@@ -222,6 +223,8 @@ def run_ours(args):
     be = pb.Backend(local_rank)
     if args.tile_impl:
         be.set_option("impl", args.tile_impl)
+    if args.linear_factorized:
+        be.set_option("linear_factorized", 1)
     if world > 1:
         be.init_comm_from_torch()
 
@@ -298,6 +301,17 @@ def run_ours(args):
     ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(ncu_path):
         traffic = json.load(open(ncu_path)).get(args.workload)
+    if t_after["impl_used"] == 3:
+        # factorised linear matvec: HBM-bound, 2 passes over X per matvec; report bytes/s of the whole matvec against the copy bandwidth
+        mv_s = (t_after["matvec_ms"] - t_before["matvec_ms"]) / max(tile_calls, 1) * 1e-3
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+        gbs = 2.0 * (N - 1) * d * npdt.itemsize / mv_s / 1e9
+        print(json.dumps({"metric": "linear_factorized_matvec", "ms_per_matvec": mv_s * 1e3, "ms_per_step": dev_ms / args.steps, "cg_iters_per_s": args.steps / (dev_ms * 1e-3),
+                          "equivalent_implicit_tflops": value, "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None},
+                          "config": {"workload": f"{args.workload}: {desc} [factorised linear fast path, SURVEY 8f row 4]"}, "n_gpus": world, "clocks": clocks.summary()}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": ("tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)") + f"<{kernel}, sym>" if tensor else "tile_kernel_simt", "peak_source": peak_src,
                 "avg_launch_ms": avg_tile_s * 1e3, "launches_timed": int(tile_calls), "flops_per_launch": F / world}

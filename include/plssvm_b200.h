@@ -52,7 +52,7 @@ typedef struct plssvm_b200_timings {
     double matvec_flops;      /* algorithmic FLOPs of ONE matvec: d * n * (n + 1)   */
     double h2d_bytes;
     double d2h_bytes;
-    int impl_used;            /* 1 = SIMT FMA tiles, 2 = tensor-core tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32) */
+    int impl_used;            /* 1 = SIMT FMA tiles, 2 = tensor-core tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32), 3 = factorised linear */
     int reserved;
 } plssvm_b200_timings;
 
@@ -62,7 +62,9 @@ int plssvm_b200_destroy(plssvm_b200_ctx *ctx);
 /* message of the last failed call on this thread (valid until the next call) */
 const char *plssvm_b200_last_error(void);
 /* tuning / debugging knobs: "impl" (0 auto, 1 simt, 2 tensor), "check_interval" (CG iterations between host polls),
- * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571) */
+ * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571), "linear_factorized" (0/1: for the linear kernel
+ * evaluate Q~ v as X (X^T v) + rank-2 terms — two streaming passes over X, O(n d) instead of O(n^2 d); default 0 = the
+ * implicit tiled formulation the reference uses) */
 int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long value);
 int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out);
 int plssvm_b200_device_count(int *count);

@@ -178,6 +178,7 @@ struct plssvm_b200_ctx {
     int impl = 0;            // 0 auto, 1 simt, 2 tensor
     int check_interval = 0;  // 0 = auto
     int verbose = 0;
+    int linear_factorized = 0;  // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     // timings of the last call
     plssvm_b200_timings tm{};
     event_pair_timer tile_timer, matvec_timer;
@@ -333,7 +334,7 @@ struct matvec_plan {
         n = static_cast<std::uint32_t>(data->N - 1);
         Tb = (n + TILE - 1) / TILE;
         pb::rank_range(pb::tri_num_tiles(Tb), c->rank, c->world, tile_lo, tile_hi);
-        partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE);
+        if (!(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
         base.A = static_cast<const T *>(data->X);
         base.B = base.A;
@@ -356,8 +357,36 @@ struct matvec_plan {
         base.done = done;
     }
 
+    // linear kernel, factorised: out = X (X^T v) + (QA_cost - q) S - q.v + v / C   — identical on every rank, no collective
+    dbuf<T> fact_w, fact_part, fact_sums;
+    void run_factorized(const T *v, T *out) {
+        cudaStream_t st = ctx->stream;
+        const std::uint32_t d = static_cast<std::uint32_t>(ds->d), ld = static_cast<std::uint32_t>(ds->ld);
+        const std::uint32_t chunks = (n + pb::W_ROWS - 1) / pb::W_ROWS;
+        if (fact_w.count == 0) {
+            fact_w.alloc(ld);
+            fact_part.alloc(static_cast<std::size_t>(chunks) * d);
+            fact_sums.alloc(2);
+            PB_CUDA(cudaMemsetAsync(fact_w.p, 0, ld * sizeof(T), st));
+        }
+        const bool timed_mv = ctx->matvec_timer.begin(st);
+        pb::w_partial_kernel<T><<<dim3((d + 255) / 256, chunks), 256, 0, st>>>(base.A, v, n, d, ld, fact_part.p);
+        pb::w_reduce_kernel<T><<<(d + 255) / 256, 256, 0, st>>>(fact_part.p, chunks, d, fact_w.p);
+        pb::linear_fact_sums_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(v, base.q, n, fact_sums.p, base.done);
+        pb::linear_fact_apply_kernel<T><<<(n + 7) / 8, 256, 0, st>>>(base.A, n, ld, fact_w.p, base.q, v, fact_sums.p, base.QA_cost, base.cost_inv, out, base.done);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches += 4;
+        if (timed_mv) { ctx->matvec_timer.end(st); }
+        ctx->tm.matvec_calls++;
+        ctx->tm.impl_used = 3;
+    }
+
     // out = Q~ v
     void run(const T *v, T *out) {
+        if (ctx->linear_factorized != 0 && base.kp.kernel == pb::K_LINEAR) {
+            run_factorized(v, out);
+            return;
+        }
         TileParams<T> p = base;
         p.v = v;
         const bool timed_mv = ctx->matvec_timer.begin(ctx->stream);
@@ -949,6 +978,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
             ctx->check_interval = static_cast<int>(value);
         } else if (k == "verbose") {
             ctx->verbose = value != 0;
+        } else if (k == "linear_factorized") {
+            ctx->linear_factorized = value != 0;
         } else {
             throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
         }

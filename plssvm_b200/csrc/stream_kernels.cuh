@@ -330,6 +330,44 @@ __global__ void w_reduce_kernel(const T *__restrict__ part, const std::uint32_t 
     w[f] = s;
 }
 
+// ---- factorised linear-kernel matvec (opt-in via option "linear_factorized") --------------------------------
+// For k(x_i, x_j) = x_i . x_j:  (Q~ v)_i = x_i . w + (QA_cost - q_i) S - q.v + v_i / C   with  w = sum_j v_j x_j,  S = sum_j v_j
+// -> two streaming passes over X (w-kernel, then this GEMV) instead of the O(n^2 d) implicit contraction.
+template <typename T>
+__global__ void __launch_bounds__(VEC_BLOCK) linear_fact_sums_kernel(const T *__restrict__ v, const T *__restrict__ q, const std::uint32_t n, T *__restrict__ sums /* S, q.v */,
+                                                                     const int *__restrict__ done) {
+    if (done != nullptr && *done != 0) { return; }
+    __shared__ T smem[VEC_BLOCK / 32];
+    T s = T(0), qv = T(0);
+    for (std::uint32_t i = threadIdx.x; i < n; i += VEC_BLOCK) {
+        s += v[i];
+        qv = pb_fma(q[i], v[i], qv);
+    }
+    s = block_sum<T, VEC_BLOCK>(s, smem);
+    qv = block_sum<T, VEC_BLOCK>(qv, smem);
+    if (threadIdx.x == 0) {
+        sums[0] = s;
+        sums[1] = qv;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) linear_fact_apply_kernel(const T *__restrict__ X, const std::uint32_t n, const std::uint32_t ld, const T *__restrict__ w, const T *__restrict__ q,
+                                                                const T *__restrict__ v, const T *__restrict__ sums, const T *__restrict__ QA_cost, const T cost_inv,
+                                                                T *__restrict__ out, const int *__restrict__ done) {
+    if (done != nullptr && *done != 0) { return; }
+    const std::size_t row = static_cast<std::size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n) { return; }
+    const int lane = threadIdx.x & 31;
+    const T *x = X + row * ld;
+    T s0 = T(0), s1 = T(0);
+    for (std::uint32_t k = 2 * lane; k < ld; k += 64) {
+        s0 = pb_fma(x[k], w[k], s0);
+        s1 = pb_fma(x[k + 1], w[k + 1], s1);
+    }
+    const T s = warp_sum(s0 + s1);
+    if (lane == 0) { out[row] = s + (*QA_cost - q[row]) * sums[0] - sums[1] + v[row] * cost_inv; }
+}
+
 // linear-kernel prediction on the device (the reference does this GEMV on the host: gpu_csvm.hpp:702-705):
 // out[p] = w . x_p - rho, one warp per point
 template <typename T>
