@@ -57,10 +57,15 @@ constexpr bool has_unnamed_arguments() {
     return (... || !detail::is_tagged_v<Args>);
 }
 
+namespace detail {
+template <typename Tag, typename... Names>
+inline constexpr bool tag_in_v = (... || std::is_same_v<Tag, typename Names::tag_type>);
+}  // namespace detail
+
 template <typename... Args, typename... Names>
 constexpr bool has_other_than(const Names &...) {
     // true if some tagged argument carries a tag that is not among Names
-    return (... || (detail::is_tagged_v<Args> && !(... || std::is_same_v<detail::tag_of_t<Args>, typename Names::tag_type>) ));
+    return (... || (detail::is_tagged_v<Args> && !detail::tag_in_v<detail::tag_of_t<Args>, Names...>) );
 }
 
 template <typename... Args>

@@ -26,6 +26,11 @@ struct parameter;
 class execution_range;
 template <typename T>
 struct tracking_entry;
+namespace cmd {
+class parser_train;
+class parser_predict;
+class parser_scale;
+}  // namespace cmd
 }  // namespace detail
 }  // namespace plssvm
 
@@ -57,5 +62,12 @@ template <>
 struct fmt::formatter<plssvm::detail::execution_range> : fmt::ostream_formatter {};
 template <typename T>
 struct fmt::formatter<plssvm::detail::tracking_entry<T>> : fmt::ostream_formatter {};
+
+template <>
+struct fmt::formatter<plssvm::detail::cmd::parser_train> : fmt::ostream_formatter {};
+template <>
+struct fmt::formatter<plssvm::detail::cmd::parser_predict> : fmt::ostream_formatter {};
+template <>
+struct fmt::formatter<plssvm::detail::cmd::parser_scale> : fmt::ostream_formatter {};
 
 #endif  // PLSSVM_B200_FMT_PRELUDE_HPP_
