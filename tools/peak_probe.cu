@@ -53,6 +53,16 @@ __global__ void __launch_bounds__(256) fma_loop(T *out, int iters) {
     if (s == T(123.456)) { out[0] = s; }
 }
 
+// uniform(-1, 1) fill (LCG): real operand bit patterns, so tensor-core GEMMs draw realistic power
+template <typename T>
+__global__ void fill_random(T *p, size_t n, unsigned seed) {
+    for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+        unsigned x = (unsigned) (i * 2654435761u) ^ seed;
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        p[i] = T((x & 0xFFFFFF) / double(0x800000) - 1.0);
+    }
+}
+
 template <typename F>
 double time_ms(F &&f, int reps, bool best) {
     cudaEvent_t e0, e1;
@@ -141,8 +151,16 @@ int main() {
         const double tf32 = time_ms(run, 5, true);
         const double ms1 = time_ms(run, 1, true);
         const double tf32_avg = time_ms(run, std::max(1, int(3000.0 / ms1)), false);
-        std::printf(" \"cublas_sgemm_fp32_tflops\": %.2f,\n \"cublas_sgemm_tf32_tflops_burst\": %.2f,\n \"cublas_sgemm_tf32_tflops_sustained_3s\": %.2f\n", 2.0 * n * n * n / fp32 * 1e-9,
+        std::printf(" \"cublas_sgemm_fp32_tflops\": %.2f,\n \"cublas_sgemm_tf32_tflops_burst\": %.2f,\n \"cublas_sgemm_tf32_tflops_sustained_3s\": %.2f,\n", 2.0 * n * n * n / fp32 * 1e-9,
                     2.0 * n * n * n / tf32 * 1e-9, 2.0 * n * n * n / tf32_avg * 1e-9);
+        // the same with uniform(-1, 1) operands: the power-limited number a real TF32 kernel can be compared with
+        fill_random<float><<<1184, 256>>>(A, size_t(n) * n, 1u);
+        fill_random<float><<<1184, 256>>>(B, size_t(n) * n, 2u);
+        CK(cudaDeviceSynchronize());
+        const double tf32_rb = time_ms(run, 5, true);
+        const double ms2 = time_ms(run, 1, true);
+        const double tf32_ravg = time_ms(run, std::max(1, int(4000.0 / ms2)), false);
+        std::printf(" \"cublas_sgemm_tf32_random_tflops_burst\": %.2f,\n \"cublas_sgemm_tf32_random_tflops_sustained_4s\": %.2f\n", 2.0 * n * n * n / tf32_rb * 1e-9, 2.0 * n * n * n / tf32_ravg * 1e-9);
         cudaFree(A); cudaFree(B); cudaFree(C);
     }
     std::printf("}\n");
