@@ -288,7 +288,7 @@ def run_ours(args):
     peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
     peak, peak_src = 37.0, "vendor figure (fallback: profiles/peaks_b200.json missing)"
     tensor = t_after["impl_used"] == 2
-    key = "dmma_tflops_sustained_3s" if dtype == "float64" else ("cublas_sgemm_tf32_tflops_sustained_3s" if tensor else "ffma_tflops")
+    key = "dmma_tflops_sustained_3s" if dtype == "float64" else ("cublas_sgemm_tf32_random_tflops_sustained_4s" if tensor else "ffma_tflops")
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))
         if key in pk:

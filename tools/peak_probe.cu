@@ -93,7 +93,7 @@ int main() {
     std::printf("{\n \"gpu\": \"%s\", \"sms\": %d,\n", prop.name, sms);
 
     // --- issue-rate probes: `wps` warps per SM sub-partition, 16 independent accumulators per warp
-    for (int wps : { 1, 2, 4 }) {
+    for (int wps : { 1, 2 }) {
         const int iters = 20000;
         const int blocks = sms, threads = 128 * wps > 1024 ? 1024 : 128 * wps;
         const int bl = 128 * wps > 1024 ? blocks * (128 * wps / 1024) : blocks;
