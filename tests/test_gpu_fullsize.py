@@ -121,6 +121,49 @@ def test_full_size_matvec_row_sampled(be, orc, workload):
     torch.cuda.empty_cache()
 
 
+@pytest.mark.parametrize("workload,eps", [("C2", 1e-8), ("C3", 1e-4)])
+def test_full_size_solve_satisfies_the_system(be, workload, eps):
+    """Full CG solve at BASELINE size; the returned alpha must satisfy the reduced system Q~ x = b~ to the stopping tolerance.
+    Checked on 512 sampled rows with torch fp64 (cuBLAS) — independent of the library — plus the structural identities
+    alpha_N = -sum(x) and rho = -(y_N + QA_cost sum(x) - q.x)  (gpu_csvm.hpp:649-653)."""
+    import torch
+    N, d, kernel, dtype, _ = WORKLOADS[workload]
+    dev = torch.device("cuda", 0)
+    X, y = make_device_data(N, d, dtype, 42 + list(WORKLOADS).index(workload), dev)
+    n = N - 1
+    gamma = 1.0 / d
+    ds = be.dataset(X)
+    yh = y.cpu().numpy()
+    r = be.solve(ds, yh, kernel, eps=eps, max_iter=200)
+    assert 1 < r["iterations"] < 200, r["iterations"]
+    assert float(r["delta"]) <= eps * eps * float(r["delta0"])
+    q, k_last = be.run_q_kernel(ds, kernel, gamma=gamma)
+    qa = float(k_last) + 1.0
+    x = r["alpha"][:n].astype(np.float64)
+    assert abs(r["alpha"][n] + x.sum()) <= 1e-6 * np.abs(x).sum()
+    bias = float(yh[n]) + qa * x.sum() - float(np.dot(q.astype(np.float64), x))
+    assert abs(-bias - float(r["rho"])) <= (1e-8 if dtype == "float64" else 1e-2) * max(1.0, abs(bias))
+    rng = np.random.default_rng(3)
+    rows = torch.from_numpy(np.sort(rng.choice(n, 512, replace=False))).to(dev)
+    K = _kernel_rows_torch(X, rows, kernel, gamma)
+    q_t = torch.from_numpy(q.astype(np.float64)).to(dev)
+    x_t = torch.from_numpy(x).to(dev)
+    Qx = (K + qa - q_t[rows][:, None] - q_t[None, :]) @ x_t + x_t[rows]  # + x / C with C = 1
+    b = (y[:n].double() - y[n].double())[rows]
+    res = float((Qx - b).norm()) / float(b.norm())
+    # r.r <= eps^2 r0.r0 bounds the residual relative to the INITIAL residual (x0 = 1), which is ~1e4 x |b~| on this data: the
+    # residual relative to |b~| may be that much larger than eps; fp32 additionally carries the rounding of a 131,071-term sum
+    bound = eps * float(np.sqrt(float(r["delta0"]))) / float(np.sqrt(n) * 1.0) * 20 + (0.0 if dtype == "float64" else 5e-2)
+    assert res <= max(bound, 1e-9), (res, bound)
+    # the model classifies a sample of its own training points consistently with the sign of the labels' majority
+    idx = torch.from_numpy(np.sort(rng.choice(N, 4096, replace=False))).to(dev)
+    vals, _ = be.predict_values(ds, r["alpha"], r["rho"], be.dataset(X[idx].contiguous()), kernel, gamma=gamma)
+    acc = float(np.mean(np.where(vals > 0, 1.0, -1.0) == y[idx].cpu().numpy()))
+    assert acc > 0.9, acc
+    del ds, X
+    torch.cuda.empty_cache()
+
+
 def test_config1_end_to_end_against_the_oracle(be, orc):
     """C1 = 5,000 x 1,000 linear fp64 eps 1e-8: the reference's own CPU-runnable configuration, full fit + predict."""
     import torch
