@@ -16,6 +16,7 @@
 #include "tile_dmma.cuh"
 #include "tile_simt.cuh"
 #include "tile_tf32.cuh"
+#include "tile_tf32_2sm.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -271,6 +272,19 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
             return;
         }
     } else {
+        if (impl == 4) {  // CTA-pair tcgen05 kernel: tile range is in 256 x 256 super-tiles, one cluster of two CTAs per SM pair
+            CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
+            make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
+            make_tensor_map<float>(ctx, &tmAlo, p.A_lo, p.n_rows, p.ld);
+            make_tensor_map<float>(ctx, &tmBhi, p.B_hi, p.n_cols, p.ld);
+            make_tensor_map<float>(ctx, &tmBlo, p.B_lo, p.n_cols, p.ld);
+            const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms / 2)));
+            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_tf32_2sm<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::TF2_SMEM_BYTES));
+            pb::tile_kernel_tf32_2sm<KERNEL, MODE><<<2 * clusters, pb::TF2_THREADS, pb::TF2_SMEM_BYTES, ctx->stream>>>(tmAhi, tmAlo, tmBhi, tmBlo, p);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+            return;
+        }
         if (impl == 2) {
             CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
             make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
@@ -291,6 +305,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx) {
+    if (ctx->impl == 4) { return sizeof(T) == 4 ? 4 : 2; }  // CTA-pair tcgen05 kernel exists for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
     return 2;  // tensor-core tiles: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
 }
@@ -325,6 +340,7 @@ struct matvec_plan {
     const plssvm_b200_dataset *ds;
     std::uint32_t n;  // N - 1
     std::uint32_t Tb; // tiles per side
+    int tile_shift = 0;
     std::uint64_t tile_lo, tile_hi;
     dbuf<T> partial;
     TileParams<T> base;
@@ -333,7 +349,8 @@ struct matvec_plan {
         ctx(c), ds(data) {
         n = static_cast<std::uint32_t>(data->N - 1);
         Tb = (n + TILE - 1) / TILE;
-        pb::rank_range(pb::tri_num_tiles(Tb), c->rank, c->world, tile_lo, tile_hi);
+        tile_shift = resolve_impl<T>(c) == 4 ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
+        pb::rank_range(pb::tri_num_tiles((Tb + tile_shift) >> tile_shift), c->rank, c->world, tile_lo, tile_hi);
         if (!(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
         base.A = static_cast<const T *>(data->X);
@@ -393,7 +410,7 @@ struct matvec_plan {
         const bool timed = ctx->tile_timer.begin(ctx->stream);
         launch_tiles<T, pb::MODE_SYM>(ctx, p);
         if (timed) { ctx->tile_timer.end(ctx->stream); }
-        pb::reduce_partials_kernel<T, pb::MODE_SYM><<<Tb, 512, 0, ctx->stream>>>(partial.p, out, n, Tb, Tb, tile_lo, tile_hi, ctx->world > 1 ? 1 : 0, T(1), T(0), 0, base.done);
+        pb::reduce_partials_kernel<T, pb::MODE_SYM><<<Tb, 512, 0, ctx->stream>>>(partial.p, out, n, Tb, Tb, tile_lo, tile_hi, ctx->world > 1 ? 1 : 0, tile_shift, T(1), T(0), 0, base.done);
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches++;
         all_reduce_sum(ctx, out, n);
@@ -693,6 +710,7 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.T_cols = (p.n_cols + TILE - 1) / TILE;
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
+    if (resolve_impl<T>(ctx) == 4) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
     p.row_sq = P_sq;
     p.col_sq = static_cast<const T *>(sv->sq);
     p.v = alpha_d;
@@ -701,7 +719,7 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     const bool timed = ctx->tile_timer.begin(ctx->stream);
     launch_tiles<T, pb::MODE_RECT>(ctx, p);
     if (timed) { ctx->tile_timer.end(ctx->stream); }
-    pb::reduce_partials_kernel<T, pb::MODE_RECT><<<p.T_rows, 512, 0, ctx->stream>>>(p.partial, out_d, p.n_rows, p.T_rows, p.T_cols, 0, p.tile_hi, 0, T(1), -rho, 0, nullptr);
+    pb::reduce_partials_kernel<T, pb::MODE_RECT><<<p.T_rows, 512, 0, ctx->stream>>>(p.partial, out_d, p.n_rows, p.T_rows, p.T_cols, 0, p.tile_hi, 0, 0, T(1), -rho, 0, nullptr);
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
 }
@@ -971,7 +989,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            PB_REQUIRE(value >= 0 && value <= 2, "impl must be 0 (auto), 1 (simt) or 2 (tensor)");
+            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4, "impl must be 0 (auto), 1 (simt), 2 (tensor) or 4 (fp32: CTA-pair tensor)");
             ctx->impl = static_cast<int>(value);
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) q_kernel(const T *__restrict__ X, const s
 template <typename T, int MODE>
 __global__ void __launch_bounds__(512) reduce_partials_kernel(const T *__restrict__ partial, T *__restrict__ out, const std::uint32_t n_out, const std::uint32_t T_rows,
                                                               const std::uint32_t T_cols, const std::uint64_t tile_lo, const std::uint64_t tile_hi, const int check_owner,
-                                                              const T scale, const T shift, const int accumulate, const int *__restrict__ done) {
+                                                              const int tile_shift /* 1: the schedule is over 2x2 super-tiles */, const T scale, const T shift,
+                                                              const int accumulate, const int *__restrict__ done) {
     if (done != nullptr && *done != 0) { return; }
     __shared__ T s_part[4][TILE];
     const int r = threadIdx.x & (TILE - 1), grp = threadIdx.x >> 7;  // 4 groups of 128 threads
@@ -85,10 +86,11 @@ __global__ void __launch_bounds__(512) reduce_partials_kernel(const T *__restric
     for (std::uint32_t B = grp; B < T_cols; B += 4) {
         if (check_owner) {
             std::uint64_t L;
+            const std::uint32_t Sr = (T_rows + tile_shift) >> tile_shift, Sc = (T_cols + tile_shift) >> tile_shift;
             if constexpr (MODE == MODE_SYM) {
-                L = A >= B ? tri_encode(T_rows, A, B) : tri_encode(T_rows, B, A);
+                L = A >= B ? tri_encode(Sr, A >> tile_shift, B >> tile_shift) : tri_encode(Sr, B >> tile_shift, A >> tile_shift);
             } else {
-                L = rect_encode(T_rows, T_cols, A, B);
+                L = rect_encode(Sr, Sc, A >> tile_shift, B >> tile_shift);
             }
             if (L < tile_lo || L >= tile_hi) { continue; }
         }
