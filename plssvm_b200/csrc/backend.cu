@@ -17,6 +17,7 @@
 #include "tile_simt.cuh"
 #include "tile_tf32.cuh"
 #include "tile_tf32_2sm.cuh"
+#include "tile_tf32_n256.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -285,6 +286,19 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
             ctx->tm.kernel_launches++;
             return;
         }
+        if (impl == 5) {  // 128 x 256 tiles per CTA: units are halves of the 256 x 256 super-tiles (tile range in super-tiles)
+            CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
+            make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
+            make_tensor_map<float>(ctx, &tmAlo, p.A_lo, p.n_rows, p.ld);
+            make_tensor_map<float>(ctx, &tmBhi, p.B_hi, p.n_cols, p.ld);
+            make_tensor_map<float>(ctx, &tmBlo, p.B_lo, p.n_cols, p.ld);
+            const unsigned g5 = static_cast<unsigned>(std::min<std::uint64_t>(2 * ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
+            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_tf32_n256<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::TN_SMEM_BYTES));
+            pb::tile_kernel_tf32_n256<KERNEL, MODE><<<g5, pb::TN_THREADS, pb::TN_SMEM_BYTES, ctx->stream>>>(tmAhi, tmAlo, tmBhi, tmBlo, p);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+            return;
+        }
         if (impl == 2) {
             CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
             make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
@@ -305,7 +319,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx) {
-    if (ctx->impl == 4) { return sizeof(T) == 4 ? 4 : 2; }  // CTA-pair tcgen05 kernel exists for fp32 only
+    if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
     return 2;  // tensor-core tiles: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
 }
@@ -349,7 +363,7 @@ struct matvec_plan {
         ctx(c), ds(data) {
         n = static_cast<std::uint32_t>(data->N - 1);
         Tb = (n + TILE - 1) / TILE;
-        tile_shift = resolve_impl<T>(c) == 4 ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
+        tile_shift = resolve_impl<T>(c) >= 4 ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
         pb::rank_range(pb::tri_num_tiles((Tb + tile_shift) >> tile_shift), c->rank, c->world, tile_lo, tile_hi);
         if (!(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
@@ -710,7 +724,7 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.T_cols = (p.n_cols + TILE - 1) / TILE;
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
-    if (resolve_impl<T>(ctx) == 4) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
+    if (resolve_impl<T>(ctx) >= 4) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
     p.row_sq = P_sq;
     p.col_sq = static_cast<const T *>(sv->sq);
     p.v = alpha_d;
@@ -989,7 +1003,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4, "impl must be 0 (auto), 1 (simt), 2 (tensor) or 4 (fp32: CTA-pair tensor)");
+            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 5, "impl must be 0 (auto), 1 (simt), 2 (tensor), 4 (fp32: CTA-pair tensor) or 5 (fp32: 128x256 tensor)");
             ctx->impl = static_cast<int>(value);
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");
