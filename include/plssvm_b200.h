@@ -64,7 +64,8 @@ const char *plssvm_b200_last_error(void);
 /* tuning / debugging knobs: "impl" (0 auto, 1 simt, 2 tensor), "check_interval" (CG iterations between host polls),
  * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571), "linear_factorized" (0/1: for the linear kernel
  * evaluate Q~ v as X (X^T v) + rank-2 terms — two streaming passes over X, O(n d) instead of O(n^2 d); default 0 = the
- * implicit tiled formulation the reference uses) */
+ * implicit tiled formulation the reference uses), "ignore_convergence" (0/1, benchmarking only: the stopping test is
+ * skipped so that exactly the requested number of CG iterations runs) */
 int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long value);
 int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out);
 int plssvm_b200_device_count(int *count);

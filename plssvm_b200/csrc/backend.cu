@@ -180,6 +180,7 @@ struct plssvm_b200_ctx {
     int impl = 0;            // 0 auto, 1 simt, 2 tensor
     int check_interval = 0;  // 0 = auto
     int verbose = 0;
+    int ignore_convergence = 0;  // benchmarking: never set the convergence flag, so exactly the requested number of iterations runs
     int linear_factorized = 0;  // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     // timings of the last call
     plssvm_b200_timings tm{};
@@ -604,7 +605,7 @@ struct cg_session : cg_session_base {
         } else {
             pb::cg_update_xr_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(x.p, r.p, dvec.p, Ad.p, n, state.p, part.p);  // x += a d; r -= a Ad (588, 611-613)
         }
-        pb::cg_beta_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p, eps, iter < TRACE_CAP ? trace.p : nullptr);                  // delta, stop test, beta (616-625)
+        pb::cg_beta_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(part.p, vblocks, state.p, eps, iter < TRACE_CAP ? trace.p : nullptr, ctx->ignore_convergence);                 // delta, stop test, beta (616-625)
         pb::cg_update_d_kernel<T, false><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);                // d = beta d + r   (627)
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += (iter % 50 == 49) ? 6 : 5;
@@ -1010,6 +1011,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
             ctx->check_interval = static_cast<int>(value);
         } else if (k == "verbose") {
             ctx->verbose = value != 0;
+        } else if (k == "ignore_convergence") {
+            ctx->ignore_convergence = value != 0;
         } else if (k == "linear_factorized") {
             ctx->linear_factorized = value != 0;
         } else {

@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(VEC_BLOCK) cg_update_xr_kernel(T *__restrict__
 
 // delta_old = delta; delta = r.r; stop test; beta   (gpu_csvm.hpp:616-625)
 template <typename T>
-__global__ void __launch_bounds__(VEC_BLOCK) cg_beta_kernel(const T *__restrict__ part, const std::uint32_t nparts, CGState<T> *st, const T eps, T *__restrict__ trace) {
+__global__ void __launch_bounds__(VEC_BLOCK) cg_beta_kernel(const T *__restrict__ part, const std::uint32_t nparts, CGState<T> *st, const T eps, T *__restrict__ trace,
+                                                            const int ignore_convergence) {
     if (st->done != 0) { return; }
     __shared__ T smem[VEC_BLOCK / 32];
     const T delta = sum_partials(part, nparts, smem);
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(VEC_BLOCK) cg_beta_kernel(const T *__restrict_
         st->delta = delta;
         st->iter += 1ull;
         if (trace != nullptr) { trace[st->iter] = delta; }
-        if (delta <= eps * eps * st->delta0) {
+        if (ignore_convergence == 0 && delta <= eps * eps * st->delta0) {
             st->done = 1;
         } else {
             st->beta = delta / delta_old;
