@@ -785,7 +785,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     constexpr std::size_t SUPER_BATCH = std::size_t{ 1 } << 22;
     const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
-    const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx) == 2;
+    const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx) >= 2;  // every tcgen05 variant (impl 2, 4, 5) consumes the hi / lo split
     if (pts_ds == nullptr) {
         const int n_stage = m > PREDICT_BATCH ? 2 : 1;
         for (int i = 0; i < n_stage; ++i) {
