@@ -107,6 +107,7 @@ tile_kernel_tf32_2sm(const __grid_constant__ CUtensorMap tmAhi, const __grid_con
     }
     tcgen05_fence_before();
     cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
+    __syncthreads();     // redundant after the cluster barrier; keeps compute-sanitizer's racecheck (which tracks bar.sync only) quiet about tmem_slot
     tcgen05_fence_after();
     const std::uint32_t tmem_base = *tmem_slot;
 
