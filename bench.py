@@ -42,7 +42,7 @@ KERNEL_IDS = {"linear": 0, "polynomial": 1, "rbf": 2}
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=60, help="timed CG iterations (default 60 = SURVEY.md §8d: with 3 warm-up iterations the timed region contains the iter % 50 == 49 residual refresh)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
@@ -353,8 +353,9 @@ def run_ours(args):
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "final_residual": float(res["delta"]), "tile_impl": int(t_after["impl_used"]), "full_solve": full,
         "precision_note": None if dtype == "float64" else "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)",
+        "matvecs_in_timed_region": int(tile_calls),
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(_finite(line)), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -442,9 +443,20 @@ def run_predict(args):
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": "tile_kernel_dmma<rbf, rect>"},
         "cpu_baseline": None,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(_finite(line)), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _finite(obj):
+    """JSON has no NaN / inf: iterations run far past convergence (fixed-count timing) may end with a non-finite residual."""
+    if isinstance(obj, float):
+        return obj if obj == obj and abs(obj) != float("inf") else None
+    if isinstance(obj, dict):
+        return {k: _finite(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_finite(v) for v in obj]
+    return obj
 
 
 def main():

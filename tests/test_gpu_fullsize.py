@@ -217,3 +217,39 @@ def test_config5_predict_sampled_against_the_oracle(be, orc):
         want = (torch.exp(-d2 / d) @ a_t - rho).cpu().numpy()
         assert np.max(np.abs(vals[c0:c0 + 16384] - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
         assert (np.where(vals[c0:c0 + 16384] > 0, 1, -1) == np.where(want > 0, 1, -1))[np.abs(want) > 1e-9].all()
+
+
+def test_config5_full_million_points_64bit_indexing(be):
+    """The whole C5 job on one GPU: 1,048,576 test points x 4,096 features (4.3e9 elements — the reference's `int` index
+    `p + (n_pts + 96) * f` overflows here, predict_kernel.cu:40-42,64-66) against 65,536 support vectors, values of sampled points
+    (including the last rows, far beyond 2^31 elements) against torch fp64."""
+    import torch
+    n_sv, d, kernel, dtype, _ = WORKLOADS["C5"]
+    dev = torch.device("cuda", 0)
+    free, _total = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~75 GB of free HBM")
+    m = 1048576
+    SV, _ = make_device_data(n_sv, d, dtype, 47, dev)
+    P, _ = make_device_data(m, d, dtype, 48, dev)
+    rng = np.random.default_rng(47)
+    alpha = rng.uniform(-1, 1, n_sv)
+    alpha -= alpha.mean()
+    rho = 0.1
+    sv_ds = be.dataset(SV)
+    p_ds = be.dataset(P)
+    idx = np.sort(np.r_[rng.choice(m, 200, replace=False), m - 1 - np.arange(56), np.arange(524288 - 4, 524288 + 4)])
+    Ps = P[torch.from_numpy(idx).to(dev)].clone()
+    del P
+    torch.cuda.empty_cache()
+    vals, _ = be.predict_values(sv_ds, alpha, rho, p_ds, kernel)
+    assert vals.shape == (m,) and np.all(np.isfinite(vals))
+    sq_sv = (SV ** 2).sum(1)
+    d2 = ((Ps ** 2).sum(1)[:, None] + sq_sv[None, :] - 2 * (Ps @ SV.T)).clamp_min(0)
+    want = (torch.exp(-d2 / d) @ torch.from_numpy(alpha).to(dev) - rho).cpu().numpy()
+    assert np.max(np.abs(vals[idx] - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
+    t = be.timings()
+    assert t["matvec_tile_ms"] > 0
+    p_ds.close()
+    sv_ds.close()
+    torch.cuda.empty_cache()
