@@ -274,12 +274,15 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
             return;
         }
     } else {
-        if (impl == 4) {  // CTA-pair tcgen05 kernel: tile range is in 256 x 256 super-tiles, one cluster of two CTAs per SM pair
-            CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
+        CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;  // TF32 hi / lo operands of the tcgen05 kernels (impl 2, 4, 5)
+        if (impl >= 2) {
+            PB_REQUIRE(p.A_hi != nullptr && p.A_lo != nullptr && p.B_hi != nullptr && p.B_lo != nullptr, "fp32 tensor path needs the hi / lo split of both operands");
             make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
             make_tensor_map<float>(ctx, &tmAlo, p.A_lo, p.n_rows, p.ld);
             make_tensor_map<float>(ctx, &tmBhi, p.B_hi, p.n_cols, p.ld);
             make_tensor_map<float>(ctx, &tmBlo, p.B_lo, p.n_cols, p.ld);
+        }
+        if (impl == 4) {  // CTA-pair tcgen05 kernel: tile range is in 256 x 256 super-tiles, one cluster of two CTAs per SM pair
             const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms / 2)));
             PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_tf32_2sm<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::TF2_SMEM_BYTES));
             pb::tile_kernel_tf32_2sm<KERNEL, MODE><<<2 * clusters, pb::TF2_THREADS, pb::TF2_SMEM_BYTES, ctx->stream>>>(tmAhi, tmAlo, tmBhi, tmBlo, p);
@@ -288,11 +291,6 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
             return;
         }
         if (impl == 5) {  // 128 x 256 tiles per CTA: units are halves of the 256 x 256 super-tiles (tile range in super-tiles)
-            CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
-            make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
-            make_tensor_map<float>(ctx, &tmAlo, p.A_lo, p.n_rows, p.ld);
-            make_tensor_map<float>(ctx, &tmBhi, p.B_hi, p.n_cols, p.ld);
-            make_tensor_map<float>(ctx, &tmBlo, p.B_lo, p.n_cols, p.ld);
             const unsigned g5 = static_cast<unsigned>(std::min<std::uint64_t>(2 * ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
             PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_tf32_n256<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::TN_SMEM_BYTES));
             pb::tile_kernel_tf32_n256<KERNEL, MODE><<<g5, pb::TN_THREADS, pb::TN_SMEM_BYTES, ctx->stream>>>(tmAhi, tmAlo, tmBhi, tmBlo, p);
@@ -301,11 +299,6 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
             return;
         }
         if (impl == 2) {
-            CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
-            make_tensor_map<float>(ctx, &tmAhi, p.A_hi, p.n_rows, p.ld);
-            make_tensor_map<float>(ctx, &tmAlo, p.A_lo, p.n_rows, p.ld);
-            make_tensor_map<float>(ctx, &tmBhi, p.B_hi, p.n_cols, p.ld);
-            make_tensor_map<float>(ctx, &tmBlo, p.B_lo, p.n_cols, p.ld);
             PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_tf32<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::TF32_SMEM_BYTES));
             pb::tile_kernel_tf32<KERNEL, MODE><<<grid, pb::TF32_THREADS, pb::TF32_SMEM_BYTES, ctx->stream>>>(tmAhi, tmAlo, tmBhi, tmBlo, p);
             PB_CUDA(cudaGetLastError());
@@ -398,14 +391,15 @@ struct matvec_plan {
         if (fact_w.count == 0) {
             fact_w.alloc(ld);
             fact_part.alloc(static_cast<std::size_t>(chunks) * d);
-            fact_sums.alloc(2);
+            fact_sums.alloc(2 * static_cast<std::size_t>((n + pb::VEC_CHUNK - 1) / pb::VEC_CHUNK));
             PB_CUDA(cudaMemsetAsync(fact_w.p, 0, ld * sizeof(T), st));
         }
         const bool timed_mv = ctx->matvec_timer.begin(st);
         pb::w_partial_kernel<T><<<dim3((d + 255) / 256, chunks), 256, 0, st>>>(base.A, v, n, d, ld, fact_part.p);
-        pb::w_reduce_kernel<T><<<(d + 255) / 256, 256, 0, st>>>(fact_part.p, chunks, d, fact_w.p);
-        pb::linear_fact_sums_kernel<T><<<1, pb::VEC_BLOCK, 0, st>>>(v, base.q, n, fact_sums.p, base.done);
-        pb::linear_fact_apply_kernel<T><<<(n + 7) / 8, 256, 0, st>>>(base.A, n, ld, fact_w.p, base.q, v, fact_sums.p, base.QA_cost, base.cost_inv, out, base.done);
+        const std::uint32_t vb = (n + pb::VEC_CHUNK - 1) / pb::VEC_CHUNK;
+        pb::w_reduce_kernel<T><<<(d + 31) / 32, 256, 0, st>>>(fact_part.p, chunks, d, fact_w.p);
+        pb::linear_fact_sums_kernel<T><<<vb, pb::VEC_BLOCK, 0, st>>>(v, base.q, n, fact_sums.p, base.done);
+        pb::linear_fact_apply_kernel<T><<<(n + 7) / 8, 256, 0, st>>>(base.A, n, ld, fact_w.p, base.q, v, fact_sums.p, vb, base.QA_cost, base.cost_inv, out, base.done);
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += 4;
         if (timed_mv) { ctx->matvec_timer.end(st); }
@@ -693,7 +687,7 @@ void run_w_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *
     PB_CUDA(cudaMemsetAsync(w_d, 0, sv->ld * sizeof(T), ctx->stream));
     const dim3 grid((d + 255) / 256, chunks);
     pb::w_partial_kernel<T><<<grid, 256, 0, ctx->stream>>>(static_cast<const T *>(sv->X), alpha_d, sv->N, d, static_cast<std::uint32_t>(sv->ld), part.p);
-    pb::w_reduce_kernel<T><<<(d + 255) / 256, 256, 0, ctx->stream>>>(part.p, chunks, d, w_d);
+    pb::w_reduce_kernel<T><<<(d + 31) / 32, 256, 0, ctx->stream>>>(part.p, chunks, d, w_d);
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches += 2;
     PB_CUDA(cudaStreamSynchronize(ctx->stream));  // `part` is freed on return

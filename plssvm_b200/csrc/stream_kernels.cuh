@@ -324,40 +324,73 @@ __global__ void __launch_bounds__(256) w_partial_kernel(const T *__restrict__ SV
     for (std::size_t i = r0; i < r1; ++i) { s = pb_fma(alpha[i], SV[i * ld + f], s); }
     part[static_cast<std::size_t>(blockIdx.y) * d + f] = s;
 }
+// stage 2: 32 features x 8 chunk groups per block; every group adds its chunks in order, the 8 group sums are added in order
 template <typename T>
-__global__ void w_reduce_kernel(const T *__restrict__ part, const std::uint32_t chunks, const std::uint32_t d, T *__restrict__ w) {
-    const std::uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= d) { return; }
+__global__ void __launch_bounds__(256) w_reduce_kernel(const T *__restrict__ part, const std::uint32_t chunks, const std::uint32_t d, T *__restrict__ w) {
+    __shared__ T s_grp[8][32];
+    const int fx = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const std::uint32_t f = blockIdx.x * 32 + fx;
     T s = T(0);
-    for (std::uint32_t c = 0; c < chunks; ++c) { s += part[static_cast<std::size_t>(c) * d + f]; }
-    w[f] = s;
+    if (f < d) {
+        for (std::uint32_t c = grp; c < chunks; c += 8) { s += part[static_cast<std::size_t>(c) * d + f]; }
+    }
+    s_grp[grp][fx] = s;
+    __syncthreads();
+    if (grp == 0 && f < d) {
+        T total = T(0);
+        #pragma unroll
+        for (int g = 0; g < 8; ++g) { total += s_grp[g][fx]; }
+        w[f] = total;
+    }
 }
 
 // ---- factorised linear-kernel matvec (opt-in via option "linear_factorized") --------------------------------
 // For k(x_i, x_j) = x_i . x_j:  (Q~ v)_i = x_i . w + (QA_cost - q_i) S - q.v + v_i / C   with  w = sum_j v_j x_j,  S = sum_j v_j
 // -> two streaming passes over X (w-kernel, then this GEMV) instead of the O(n^2 d) implicit contraction.
+// block partials of S = sum(v) and q.v (finished in fixed order by every block of the apply kernel)
 template <typename T>
-__global__ void __launch_bounds__(VEC_BLOCK) linear_fact_sums_kernel(const T *__restrict__ v, const T *__restrict__ q, const std::uint32_t n, T *__restrict__ sums /* S, q.v */,
+__global__ void __launch_bounds__(VEC_BLOCK) linear_fact_sums_kernel(const T *__restrict__ v, const T *__restrict__ q, const std::uint32_t n, T *__restrict__ part /* [2][blocks] */,
                                                                      const int *__restrict__ done) {
     if (done != nullptr && *done != 0) { return; }
     __shared__ T smem[VEC_BLOCK / 32];
     T s = T(0), qv = T(0);
-    for (std::uint32_t i = threadIdx.x; i < n; i += VEC_BLOCK) {
-        s += v[i];
-        qv = pb_fma(q[i], v[i], qv);
+    const std::uint32_t base = blockIdx.x * VEC_CHUNK + threadIdx.x;
+    #pragma unroll
+    for (int e = 0; e < VEC_PER_THREAD; ++e) {
+        const std::uint32_t i = base + e * VEC_BLOCK;
+        if (i < n) {
+            s += v[i];
+            qv = pb_fma(q[i], v[i], qv);
+        }
     }
     s = block_sum<T, VEC_BLOCK>(s, smem);
     qv = block_sum<T, VEC_BLOCK>(qv, smem);
     if (threadIdx.x == 0) {
-        sums[0] = s;
-        sums[1] = qv;
+        part[blockIdx.x] = s;
+        part[gridDim.x + blockIdx.x] = qv;
     }
 }
 template <typename T>
 __global__ void __launch_bounds__(256) linear_fact_apply_kernel(const T *__restrict__ X, const std::uint32_t n, const std::uint32_t ld, const T *__restrict__ w, const T *__restrict__ q,
-                                                                const T *__restrict__ v, const T *__restrict__ sums, const T *__restrict__ QA_cost, const T cost_inv,
-                                                                T *__restrict__ out, const int *__restrict__ done) {
+                                                                const T *__restrict__ v, const T *__restrict__ part, const std::uint32_t nparts, const T *__restrict__ QA_cost,
+                                                                const T cost_inv, T *__restrict__ out, const int *__restrict__ done) {
     if (done != nullptr && *done != 0) { return; }
+    __shared__ T smem[256 / 32];
+    __shared__ T sums[2];
+    {   // S and q.v from the block partials, same fixed order in every block
+        T a = T(0), b = T(0);
+        for (std::uint32_t i = threadIdx.x; i < nparts; i += 256) {
+            a += part[i];
+            b += part[nparts + i];
+        }
+        a = block_sum<T, 256>(a, smem);
+        b = block_sum<T, 256>(b, smem);
+        if (threadIdx.x == 0) {
+            sums[0] = a;
+            sums[1] = b;
+        }
+        __syncthreads();
+    }
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= n) { return; }
     const int lane = threadIdx.x & 31;
