@@ -146,8 +146,8 @@ def cpu_matvec_sample(kind_pref, d, kernel, dtype, budget_s, threads=None):
     import oracle
     kind = kind_pref if oracle.available(kind_pref) else "port"
     orc = oracle.Oracle(kind)
-    if threads:
-        orc.set_threads(threads)
+    # all host threads this process may use — torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm single-threaded
+    orc.set_threads(threads or len(os.sched_getaffinity(0)))
     cores = orc.max_threads()
     kid = KERNEL_IDS[kernel]
 
