@@ -57,6 +57,23 @@ int run(const plssvm::b200::csvm &svm, const plssvm::b200::kernel_function_type 
         std::printf("size mismatch not detected\n");
         ++failures;
     } catch (const backend_exception &) {}
+    try {  // ragged rows ("All data points must have the same number of features!", gpu_csvm.hpp:486)
+        std::vector<std::vector<T>> ragged = A;
+        ragged[2].pop_back();
+        (void) svm.solve_system_of_linear_equations(params, ragged, rhs, T{ 0.1 }, 4ull);
+        std::printf("ragged rows not detected\n");
+        ++failures;
+    } catch (const backend_exception &) {}
+    try {  // empty data ("The data must not be empty!", gpu_csvm.hpp:484)
+        (void) svm.solve_system_of_linear_equations(params, std::vector<std::vector<T>>{}, std::vector<T>{}, T{ 0.1 }, 4ull);
+        std::printf("empty data not detected\n");
+        ++failures;
+    } catch (const backend_exception &) {}
+    try {  // max_iter == 0 (gpu_csvm.hpp:489)
+        (void) svm.solve_system_of_linear_equations(params, A, rhs, T{ 0.1 }, 0ull);
+        std::printf("max_iter = 0 not detected\n");
+        ++failures;
+    } catch (const backend_exception &) {}
     try {
         (void) svm.solve_system_of_linear_equations(params, A, rhs, T{ 0 }, 4ull);
         std::printf("eps = 0 not detected\n");
