@@ -346,6 +346,27 @@ def run_ours(args):
         cpu_baseline = {"value": d * float(n_rows) * (n_rows + 1) / t_cpu / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "reference" if kind == "reference" else "port",
                         "sample": f"one OpenMP matvec on the leading {n_rows} rows x {d} features ({t_cpu:.1f} s); same kernel / real type"}
 
+    # optional second baseline: the reference's own CUDA kernel on this GPU, on a slice of the workload
+    ref_cuda = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            import oracle
+            if oracle.RefCuda.available():
+                rows = min(N, 8192 + 1)
+                Xs, _ = make_device_data(rows, d, dtype, 4242, device)
+                ds_s = be.dataset(Xs)
+                q_s, k_s = be.run_q_kernel(ds_s, kernel)
+                v_s = np.ones(rows - 1, npdt)
+                _, ms_ref = oracle.RefCuda().matvec(KERNEL_IDS[kernel], Xs, q_s, v_s, np.zeros(rows - 1, npdt), float(k_s) + 1.0, 1.0, 1.0, gamma=1.0 / d, reps=3)
+                be.run_svm_kernel(ds_s, q_s, v_s, np.zeros(rows - 1, npdt), float(k_s) + 1.0, 1.0, 1.0, kernel)
+                ms_ours = be.timings()["matvec_tile_ms"]
+                Fs = matvec_flops(rows, d)
+                ref_cuda = {"what": "reference CUDA kernel (svm_kernel.cu, compiled unchanged for sm_100, reference grid/layout) vs ours, one matvec on the same B200",
+                            "rows": rows, "features": d, "reference_ms": ms_ref, "reference_tflops": Fs / ms_ref / 1e9, "ours_ms": ms_ours, "ours_tflops": Fs / ms_ours / 1e9}
+                ds_s.close()
+        except Exception as e:  # the baseline is optional: never fail the benchmark because of it
+            ref_cuda = {"error": str(e)[:200]}
+
     line = {
         "metric": "cg_matvec_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
@@ -355,7 +376,7 @@ def run_ours(args):
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "final_residual": float(res["delta"]), "tile_impl": int(t_after["impl_used"]), "full_solve": full,
         "precision_note": None if dtype == "float64" else "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)",
-        "matvecs_in_timed_region": int(tile_calls),
+        "matvecs_in_timed_region": int(tile_calls), "reference_cuda_baseline": ref_cuda,
     }
     print(json.dumps(_finite(line)), flush=True)
     if world > 1:

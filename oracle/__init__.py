@@ -170,3 +170,39 @@ class Oracle:
 def sign_labels(values: np.ndarray) -> np.ndarray:
     """csvm.hpp:337-340 + operators.hpp:178-181: label = value > 0 ? +1 : -1 (0 maps to -1)."""
     return np.where(values > 0, 1, -1).astype(np.int32)
+
+
+class RefCuda:
+    """The reference's OWN CUDA kernels (src/plssvm/backends/CUDA/svm_kernel.cu, compiled unchanged for sm_100 by `make -C oracle
+    refcuda`) launched with the reference's layout and grid (oracle/ref_cuda_harness.cu): a second oracle on the GPU and the
+    GPU-vs-GPU baseline of bench.py.  Test / baseline infrastructure only."""
+
+    PATH = os.path.join(_HERE, "_ref", "libref_cuda.so")
+
+    @classmethod
+    def available(cls) -> bool:
+        return os.path.exists(cls.PATH)
+
+    def __init__(self):
+        self.lib = ctypes.CDLL(self.PATH)
+        vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+        for suf, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            getattr(self.lib, f"refcuda_matvec_{suf}").argtypes = [i32, vp, sz, sz, vp, vp, ct, ct, ct, i32, ct, ct, vp, vp, i32]
+
+    def matvec(self, kernel: int, X_cuda, q, v, ret, QA_cost, cost_inv, add, degree=3, gamma=1.0, coef0=0.0, reps=1):
+        """X_cuda: contiguous CUDA torch tensor (N x d).  Returns (ret + add * Q~ v, milliseconds per launch)."""
+        import torch
+        assert X_cuda.is_cuda and X_cuda.is_contiguous()
+        torch.cuda.synchronize()
+        N, d = X_cuda.shape
+        dt = np.float64 if X_cuda.dtype == torch.float64 else np.float32
+        suf = "f64" if dt == np.float64 else "f32"
+        q = np.ascontiguousarray(q, dtype=dt)
+        v = np.ascontiguousarray(v, dtype=dt)
+        out = np.array(ret, dtype=dt, copy=True)
+        ms = ctypes.c_float(0)
+        rc = getattr(self.lib, f"refcuda_matvec_{suf}")(kernel, ctypes.c_void_p(X_cuda.data_ptr()), N, d, q.ctypes.data_as(ctypes.c_void_p), v.ctypes.data_as(ctypes.c_void_p),
+                                                        QA_cost, cost_inv, add, degree, gamma, coef0, out.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ms), reps)
+        if rc != 0:
+            raise RuntimeError(f"refcuda_matvec failed with code {rc}")
+        return out, float(ms.value)
