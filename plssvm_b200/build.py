@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libplssvm_b200.so")
 SOURCES = ["backend.cu"]
-HEADERS = ["common.cuh", "tile_order.hpp", "tile_simt.cuh", "tile_dmma.cuh", "stream_kernels.cuh", os.path.join("..", "..", "include", "plssvm_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))) + [os.path.join("..", "..", "include", "plssvm_b200.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-shared", "--expt-relaxed-constexpr",

@@ -18,6 +18,7 @@
 #include "tile_tf32.cuh"
 #include "tile_tf32_2sm.cuh"
 #include "tile_tf32_n256.cuh"
+#include "tile_i8.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -177,7 +178,7 @@ struct plssvm_b200_ctx {
     int rank = 0, world = 1;
     nccl_api::comm_t comm = nullptr;
     // options
-    int impl = 0;            // 0 auto, 1 simt, 2 tensor
+    int impl = 0;            // 0 auto, 1 simt, 2 tensor, 4 / 5 fp32 tcgen05 variants, 6 fp64 through int8 slices on tcgen05 (tile_i8.cuh)
     int check_interval = 0;  // 0 = auto
     int verbose = 0;
     int ignore_convergence = 0;  // benchmarking: never set the convergence flag, so exactly the requested number of iterations runs
@@ -192,7 +193,7 @@ struct plssvm_b200_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_computed[2] = { nullptr, nullptr };
     // grow-only device workspaces kept across calls (cudaMalloc / cudaFree of 100+ MB buffers costs milliseconds and synchronises)
-    enum ws_slot { WS_PARTIAL = 0, WS_OUT, WS_ALPHA, WS_W, WS_STAGE0, WS_STAGE1, WS_SQ0, WS_SQ1, WS_HI0, WS_HI1, WS_LO0, WS_LO1, WS_COUNT };
+    enum ws_slot { WS_PARTIAL = 0, WS_OUT, WS_ALPHA, WS_W, WS_STAGE0, WS_STAGE1, WS_SQ0, WS_SQ1, WS_HI0, WS_HI1, WS_LO0, WS_LO1, WS_I8_0, WS_I8_1, WS_SC0, WS_SC1, WS_COUNT };
     void *ws_ptr[WS_COUNT] = {};
     std::size_t ws_bytes[WS_COUNT] = {};
 };
@@ -204,6 +205,9 @@ struct plssvm_b200_dataset {
     void *X = nullptr;   // [N][ld]
     void *sq = nullptr;  // [N]
     void *X_hi = nullptr, *X_lo = nullptr;  // fp32 only: TF32 hi / lo split of X for the 3xTF32 tensor path
+    // fp64 only, created on first use by the int8-slice tensor path (impl 6): digit planes [I8_S][N][ld8] and row scales
+    void *X_i8 = nullptr, *rscale = nullptr;
+    std::size_t ld8 = 0;
 };
 
 namespace {
@@ -257,12 +261,55 @@ void make_tensor_map(plssvm_b200_ctx *ctx, CUtensorMap *tm, const T *base, const
     if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(rc))); }
 }
 
+// 3-D map over the int8 digit planes [I8_S][rows][ld8]: box = 64 bytes x `box_rows` rows x all planes, 64-byte swizzle
+void make_tensor_map_i8(plssvm_b200_ctx *ctx, CUtensorMap *tm, const std::int8_t *base, const std::size_t rows, const std::size_t ld8, const std::size_t plane_bytes,
+                        const std::uint32_t box_rows) {
+    const cuuint64_t dims[3] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(pb::I8_S) };
+    const cuuint64_t strides[2] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(plane_bytes) };
+    const cuuint32_t box[3] = { static_cast<cuuint32_t>(pb::I8_BK), box_rows, static_cast<cuuint32_t>(pb::I8_S) };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<std::int8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes) failed with code " + std::to_string(static_cast<int>(rc))); }
+}
+
+inline std::size_t pitch_i8(const std::size_t d) { return (d + 127) / 128 * 128; }
+
+// fp64 rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold I8_S * rows * ld8 bytes
+void run_split_i8(plssvm_b200_ctx *ctx, const double *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8,
+                  double *rscale, cudaStream_t st) {
+    pb::split_i8_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(X, rows, static_cast<std::uint32_t>(d), static_cast<std::uint32_t>(ld), planes, rows * ld8,
+                                                                              static_cast<std::uint32_t>(ld8), rscale);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
+}
+
+// digit planes of a resident fp64 data set, created on first use
+void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
+    if (ds->X_i8 != nullptr) { return; }
+    ds->ld8 = pitch_i8(ds->d);
+    PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(pb::I8_S) * ds->N * ds->ld8));
+    PB_CUDA(cudaMalloc(&ds->rscale, ds->N * sizeof(double)));
+    run_split_i8(ctx, static_cast<const double *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<double *>(ds->rscale), ctx->stream);
+}
+
 template <typename T, int KERNEL, int MODE>
 void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
     const std::uint64_t ntiles = p.tile_hi - p.tile_lo;
     if (ntiles == 0) { return; }
     const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
     if constexpr (sizeof(T) == 8) {
+        if (impl == 6) {  // int8-slice tcgen05 tiles: units of 128 x 64, S exact int32 accumulators in TMEM
+            PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
+            CUtensorMap tmA, tmB;
+            make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE));
+            make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(pb::I8_NH));
+            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_i8<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::I8_SMEM_BYTES));
+            pb::tile_kernel_i8<KERNEL, MODE><<<grid, pb::I8_THREADS, pb::I8_SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+            return;
+        }
         if (impl == 2) {
             CUtensorMap tmA, tmB;
             make_tensor_map<double>(ctx, &tmA, p.A, p.n_rows, p.ld);
@@ -312,7 +359,9 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 }
 
 template <typename T>
-int resolve_impl(const plssvm_b200_ctx *ctx) {
+int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
+    // int8-slice tcgen05 tiles exist for fp64 only; beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA tiles
+    if (ctx->impl == 6) { return (sizeof(T) == 8 && features <= pb::I8_MAX_FEATURES) ? 6 : 2; }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
     return 2;  // tensor-core tiles: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
@@ -320,7 +369,7 @@ int resolve_impl(const plssvm_b200_ctx *ctx) {
 
 template <typename T, int MODE>
 void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p) {
-    const int impl = resolve_impl<T>(ctx);
+    const int impl = resolve_impl<T>(ctx, p.ld);
     ctx->tm.impl_used = impl;
     switch (p.kp.kernel) {
         case pb::K_LINEAR: launch_tiles_t<T, pb::K_LINEAR, MODE>(ctx, p, impl); break;
@@ -357,7 +406,8 @@ struct matvec_plan {
         ctx(c), ds(data) {
         n = static_cast<std::uint32_t>(data->N - 1);
         Tb = (n + TILE - 1) / TILE;
-        tile_shift = resolve_impl<T>(c) >= 4 ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
+        const int impl = resolve_impl<T>(c, data->ld);
+        tile_shift = (impl == 4 || impl == 5) ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
         pb::rank_range(pb::tri_num_tiles((Tb + tile_shift) >> tile_shift), c->rank, c->world, tile_lo, tile_hi);
         if (!(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
@@ -365,6 +415,15 @@ struct matvec_plan {
         base.B = base.A;
         base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
         base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
+        if constexpr (sizeof(T) == 8) {
+            if (impl == 6 && !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) {
+                ensure_i8(c, const_cast<plssvm_b200_dataset *>(data));
+                base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
+                base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
+                base.A_plane = base.B_plane = data->N * data->ld8;
+                base.ld8 = static_cast<std::uint32_t>(data->ld8);
+            }
+        }
         base.n_rows = n;
         base.n_cols = n;
         base.ld = static_cast<std::uint32_t>(data->ld);
@@ -508,6 +567,8 @@ plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const T *X, const std:
         cudaFree(ds->sq);
         cudaFree(ds->X_hi);
         cudaFree(ds->X_lo);
+        cudaFree(ds->X_i8);
+        cudaFree(ds->rscale);
         delete ds;
         throw;
     }
@@ -697,7 +758,7 @@ void run_w_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *
 // points: `pts` rows [p0, p0 + m) of a resident matrix; out_d: m values on the device
 template <typename T>
 void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, const T *w_d, const T rho, const T *P, const T *P_sq, const T *P_hi,
-                         const T *P_lo, const std::size_t m, const KernelParams<T> &kp, T *out_d) {
+                         const T *P_lo, const std::int8_t *P_i8, const T *P_scale, const std::size_t P_plane, const std::size_t m, const KernelParams<T> &kp, T *out_d) {
     const std::uint32_t ld = static_cast<std::uint32_t>(sv->ld);
     if (kp.kernel == pb::K_LINEAR) {
         pb::linear_predict_kernel<T><<<static_cast<unsigned>((m + 7) / 8), 256, 0, ctx->stream>>>(P, m, ld, w_d, rho, out_d);
@@ -719,7 +780,21 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.T_cols = (p.n_cols + TILE - 1) / TILE;
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
-    if (resolve_impl<T>(ctx) >= 4) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
+    const int impl = resolve_impl<T>(ctx, ld);
+    if (impl == 4 || impl == 5) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
+    if constexpr (sizeof(T) == 8) {
+        if (impl == 6) {
+            PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
+            ensure_i8(ctx, const_cast<plssvm_b200_dataset *>(sv));
+            p.A_i8 = P_i8;
+            p.A_scale = P_scale;
+            p.A_plane = P_plane;
+            p.B_i8 = static_cast<const std::int8_t *>(sv->X_i8);
+            p.B_scale = static_cast<const T *>(sv->rscale);
+            p.B_plane = sv->N * sv->ld8;
+            p.ld8 = static_cast<std::uint32_t>(sv->ld8);
+        }
+    }
     p.row_sq = P_sq;
     p.col_sq = static_cast<const T *>(sv->sq);
     p.v = alpha_d;
@@ -780,6 +855,13 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
     const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx) >= 2;  // every tcgen05 variant (impl 2, 4, 5) consumes the hi / lo split
+    const bool need_i8 = sizeof(T) == 8 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx, sv->ld) == 6;  // int8 digit planes of the points (tile_i8.cuh)
+    const std::size_t ld8 = pitch_i8(sv->d);
+    std::int8_t *stage_i8[2] = { nullptr, nullptr };
+    T *stage_sc[2] = { nullptr, nullptr };
+    if (need_i8 && pts_ds != nullptr) {
+        if constexpr (sizeof(T) == 8) { ensure_i8(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
+    }
     if (pts_ds == nullptr) {
         const int n_stage = m > PREDICT_BATCH ? 2 : 1;
         for (int i = 0; i < n_stage; ++i) {
@@ -788,6 +870,10 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
             if (need_split) {
                 stage_hi[i] = workspace<T>(ctx, ctx_t::WS_HI0 + i, stage_rows * sv->ld);
                 stage_lo[i] = workspace<T>(ctx, ctx_t::WS_LO0 + i, stage_rows * sv->ld);
+            }
+            if (need_i8) {
+                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8_S) * stage_rows * ld8);
+                stage_sc[i] = workspace<T>(ctx, ctx_t::WS_SC0 + i, stage_rows);
             }
             if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X[i], 0, stage_rows * sv->ld * sizeof(T), st)); }  // pad columns stay zero
         }
@@ -803,9 +889,17 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
             const T *P;
             const T *P_sq;
             const T *P_hi = nullptr, *P_lo = nullptr;
+            const std::int8_t *P_i8 = nullptr;
+            const T *P_scale = nullptr;
+            std::size_t P_plane = 0;
             if (pts_ds != nullptr) {
                 P = static_cast<const T *>(pts_ds->X) + p0 * pts_ds->ld;
                 P_sq = static_cast<const T *>(pts_ds->sq) + p0;
+                if (need_i8) {
+                    P_i8 = static_cast<const std::int8_t *>(pts_ds->X_i8) + p0 * pts_ds->ld8;
+                    P_scale = static_cast<const T *>(pts_ds->rscale) + p0;
+                    P_plane = pts_ds->N * pts_ds->ld8;
+                }
                 if (pts_ds->X_hi != nullptr) {
                     P_hi = static_cast<const T *>(pts_ds->X_hi) + p0 * pts_ds->ld;
                     P_lo = static_cast<const T *>(pts_ds->X_lo) + p0 * pts_ds->ld;
@@ -831,12 +925,20 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                         ctx->tm.kernel_launches++;
                     }
                 }
+                if constexpr (sizeof(T) == 8) {
+                    if (need_i8) {
+                        run_split_i8(ctx, stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], st);
+                        P_i8 = stage_i8[buf];
+                        P_scale = stage_sc[buf];
+                        P_plane = mb * ld8;
+                    }
+                }
                 P = stage_X[buf];
                 P_sq = stage_sq[buf];
                 P_hi = stage_hi[buf];
                 P_lo = stage_lo[buf];
             }
-            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, mb, kp, out_d + (p0 - s0));
+            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, P_i8, P_scale, P_plane, mb, kp, out_d + (p0 - s0));
             if (pts_ds == nullptr) { PB_CUDA(cudaEventRecord(ctx->ev_computed[batch_index & 1], st)); }
         }
         PB_CUDA(cudaMemcpyAsync(out + s0, out_d, ms * sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -998,7 +1100,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 5, "impl must be 0 (auto), 1 (simt), 2 (tensor), 4 (fp32: CTA-pair tensor) or 5 (fp32: 128x256 tensor)");
+            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 5 || value == 6,
+                       "impl must be 0 (auto), 1 (simt), 2 (tensor), 4 (fp32: CTA-pair tensor), 5 (fp32: 128x256 tensor) or 6 (fp64: int8-slice tcgen05 tensor)");
             ctx->impl = static_cast<int>(value);
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");
@@ -1066,6 +1169,8 @@ int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
         cudaFree(ds->sq);
         cudaFree(ds->X_hi);
         cudaFree(ds->X_lo);
+        cudaFree(ds->X_i8);
+        cudaFree(ds->rscale);
         delete ds;
     });
 }

@@ -1,0 +1,356 @@
+// fp64-accurate tile kernel of the implicit kernel matrix on the 5th-generation tensor cores: tcgen05.mma kind::i8 over
+// int8 slices of X (an Ozaki-style error-free splitting), exact int32 accumulation in TMEM, fp64 recombination in the epilogue.
+//
+// Why: tcgen05.mma has no f64 kind and the FP64 pipes of B200 (DMMA == DFMA) stop at ~37 TFLOP/s; the int8 tensor pipe is
+// ~120x faster.  Every row x_i is written once per data set (split_i8_kernel) as a fixed-point number relative to its own
+// largest element:   x_ik = 2^(e_i - (8S-2)) * sum_p a_p(i,k) 2^(8p),   a_p in [-128, 127]  (balanced base-256 digits),
+// i.e. 8S - 2 = 54 fractional bits for S = 7 slices.  Then
+//     x_i . x_j = 2^(e_i + e_j - 12) * sum_{t'=0}^{S-1} 2^(-8 (S-1-t')) * ACC_t',      ACC_t' = sum_{p+q = t'+S-1} a_p(i,:) . a_q(j,:)
+// where only the S most significant digit diagonals p + q >= S - 1 are kept (S (S+1) / 2 = 28 int8 products instead of S^2;
+// the dropped ones are below 2^-51 of |x_i|_max |x_j|_max d).  Each ACC_t' is an EXACT integer (|ACC| < 2^31 for d <= 16384),
+// so the only roundings are the S fp64 FMAs that recombine the diagonals: measured error 7e-18 |x_i||x_j| at d = 4096 —
+// below that of a native fp64 dot product (4e-17).
+//
+// Tensor-core mapping (what makes it fast): the S accumulators of a 128 x 64 output block sit side by side in TMEM
+// (column t' * 64), and the B slices sit side by side in shared memory in q order, so ONE tcgen05.mma with N = 64 * m multiplies
+// slice A_p with the m consecutive slices B_q .. B_(q+m-1) and lands in the m consecutive accumulators t' .. t'+m-1:
+// 10 wide MMAs (N up to 256) per 32-feature step instead of 28 narrow ones, which cuts the shared-memory operand traffic
+// from 168 KB to 96 KB per step (107 B/clk at the tensor pipe's pace — under the 128 B/clk the SM can deliver).
+//   * warp 0: TMA producer — per 64-feature slab two 3-D boxes {64 B, rows, S slices}, SWIZZLE_64B: A = 128 rows (56 KB),
+//     B = 64 rows (28 KB); 2-stage ring
+//   * warp 1: allocates all 512 TMEM columns (S x 64 int32 accumulator columns) and issues the MMAs from one elected lane
+//   * warps 2-9: epilogue, one accumulator row and 32 columns per thread: tcgen05.ld, int32 -> fp64 without I2F (exponent
+//     trick), Horner recombination, hand TMEM back to the MMA warp, then kernel function, QA_cost - q_i - q_j (+ 1/C on the
+//     diagonal), v-weighted row sums and mirrored column sums exactly as in the other tile kernels
+// A logical 128 x 128 tile of the schedule (tile_order.hpp) is processed as two 128 x 64 units, so tile ownership, the partial
+// buffer and the fixed-order reduction are shared with the DMMA kernel.
+// Replaces device_kernel_{linear,polynomial,rbf}<double> (reference svm_kernel.cu:17-222) and device_kernel_predict_*<double>.
+#pragma once
+
+#include "common.cuh"
+#include "tile_dmma.cuh"  // mbarrier / TMA helpers
+#include "tile_tf32.cuh"  // tcgen05 helpers
+
+namespace pb {
+
+constexpr int I8_S = 7;                                    // int8 slices per operand (8 S - 2 = 54 fractional bits)
+constexpr int I8_BK = 64;                                  // bytes (= features) per slab: one SWIZZLE_64B row, two K = 32 MMA steps
+constexpr int I8_NH = 64;                                  // columns per unit (half a tile)
+constexpr int I8_STAGES = 2;
+constexpr int I8_A_SLICE = TILE * I8_BK;                   // 8 KiB
+constexpr int I8_B_SLICE = I8_NH * I8_BK;                  // 4 KiB
+constexpr int I8_A_BYTES = I8_S * I8_A_SLICE;              // 56 KiB
+constexpr int I8_B_BYTES = I8_S * I8_B_SLICE;              // 28 KiB
+constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;    // 84 KiB
+constexpr int I8_THREADS = 320;                            // producer warp, MMA warp, 8 epilogue warps
+constexpr int I8_EPI_THREADS = 256;
+constexpr int I8_VEC_BYTES = (4 * TILE + 4 * I8_NH + 4 * I8_NH + TILE) * 8;  // row vectors, column vectors, column sums, row sums
+constexpr int I8_SMEM_BYTES = 1024 + I8_STAGES * I8_STAGE_BYTES + I8_VEC_BYTES + (2 * I8_STAGES + 2) * 8 + 16;
+constexpr std::uint32_t I8_TMEM_COLS = 512;
+constexpr std::uint32_t I8_MAX_FEATURES = 16384;           // 7 products of <= 2^14 per feature and diagonal stay below 2^31
+
+static_assert(I8_S * I8_NH <= 512, "accumulators must fit into TMEM");
+static_assert(I8_STAGE_BYTES % 1024 == 0, "stage alignment");
+
+// ---- operand preparation: fp64 rows -> S int8 digit planes + per-row scale ------------------------------------------------
+// planes[p][row][k] (row pitch ld8 bytes, zero padded), rscale[row] = 2^(e_row - 6); one warp per row
+__global__ void __launch_bounds__(256) split_i8_kernel(const double *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
+                                                       std::int8_t *__restrict__ planes, const std::size_t plane_stride, const std::uint32_t ld8,
+                                                       double *__restrict__ rscale) {
+    const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) { return; }
+    const int lane = threadIdx.x & 31;
+    const double *x = X + row * ld;
+    double mx = 0.0;
+    for (std::uint32_t k = lane; k < d; k += 32) { mx = fmax(mx, fabs(x[k])); }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    int e = 0;
+    if (mx > 0.0) { (void) frexp(mx, &e); }  // mx = m 2^e, m in [0.5, 1)  =>  |x_k| < 2^e
+    e = e < -900 ? -900 : e;
+    const double to_fixed = ldexp(1.0, (8 * I8_S - 2) - e);
+    if (lane == 0) { rscale[row] = ldexp(1.0, e - 6); }
+    std::int8_t *out = planes + row * ld8;
+    for (std::uint32_t k0 = 4u * lane; k0 < ld8; k0 += 128u) {
+        long long v[4];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { v[j] = (k0 + j < d) ? __double2ll_rn(x[k0 + j] * to_fixed) : 0ll; }
+        #pragma unroll
+        for (int p = 0; p < I8_S; ++p) {
+            std::uint32_t word = 0;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long a = (p == I8_S - 1) ? v[j] : static_cast<long long>(static_cast<signed char>(v[j] & 0xFF));  // balanced digit in [-128, 127]
+                word |= (static_cast<std::uint32_t>(a) & 0xFFu) << (8 * j);
+                v[j] = (v[j] - a) >> 8;  // exact
+            }
+            *reinterpret_cast<std::uint32_t *>(out + static_cast<std::size_t>(p) * plane_stride + k0) = word;
+        }
+    }
+}
+
+// ---- tcgen05 kind::i8 helpers -----------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor: K-major operand, 64-byte swizzle, 8-row groups 512 bytes apart
+__device__ __forceinline__ std::uint64_t umma_desc_sw64(const std::uint32_t smem_addr) {
+    return static_cast<std::uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<std::uint64_t>(1) << 16) | (static_cast<std::uint64_t>(512 >> 4) << 32) |
+           (static_cast<std::uint64_t>(1) << 46) | (static_cast<std::uint64_t>(4) << 61);
+}
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 128, N = n
+__host__ __device__ constexpr std::uint32_t i8_idesc(const std::uint32_t n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | (static_cast<std::uint32_t>(TILE >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8(const std::uint32_t tmem_d, const std::uint64_t adesc, const std::uint64_t bdesc, const std::uint32_t idesc, const std::uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const std::uint32_t dst, const CUtensorMap *tm, const int c0, const int c1, const int c2, const std::uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x8(const std::uint32_t taddr, std::uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// exact int32 -> fp64 on the FP64 add pipe: (2^52 + 2^31 + a) - (2^52 + 2^31)
+__device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __hiloint2double(0x43300000, static_cast<int>(a ^ 0x80000000u)) - 4503601774854144.0; }
+
+template <int KERNEL, int MODE>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<double> p) {
+    extern __shared__ unsigned char smem_raw[];
+    if (p.done != nullptr && *p.done != 0) { return; }
+
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *stages = smem;
+    double *s_row = reinterpret_cast<double *>(smem + I8_STAGES * I8_STAGE_BYTES);  // [4][TILE]: q_i, v_i, sq_i, scale_i
+    double *s_col = s_row + 4 * TILE;                                                // [4][I8_NH]: q_j, v_j, sq_j, scale_j
+    double *s_colsum = s_col + 4 * I8_NH;                                            // [4][I8_NH]
+    double *s_rowsum = s_colsum + 4 * I8_NH;                                         // [TILE]
+    std::uint64_t *bars = reinterpret_cast<std::uint64_t *>(s_rowsum + TILE);        // full[S], empty[S], tmem_full, tmem_empty
+    std::uint32_t *tmem_slot = reinterpret_cast<std::uint32_t *>(bars + 2 * I8_STAGES + 2);
+    const std::uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + I8_STAGES);
+    const std::uint32_t tfull = smem_u32(bars + 2 * I8_STAGES), tempty = smem_u32(bars + 2 * I8_STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const std::uint32_t num_slabs = (p.ld8 + I8_BK - 1) / I8_BK;
+
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < I8_STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, I8_EPI_THREADS / 32);  // one arrive per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(I8_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const std::uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            std::uint32_t stage = 0, phase = 0;
+            for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
+                std::uint32_t I, J;
+                if constexpr (MODE == MODE_SYM) {
+                    tri_decode(p.T_rows, L, I, J);
+                } else {
+                    rect_decode(p.T_rows, p.T_cols, L, I, J);
+                }
+                for (int h = 0; h < 2; ++h) {
+                    const int ra = static_cast<int>(I * TILE), rb = static_cast<int>(J * TILE + h * I8_NH);
+                    for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                        const std::uint32_t dst = smem_u32(stages + stage * I8_STAGE_BYTES);
+                        const std::uint32_t bar = full0 + 8 * stage;
+                        mbar_arrive_expect_tx(bar, I8_STAGE_BYTES);
+                        tma_load_3d(dst, &tmA, static_cast<int>(ks * I8_BK), ra, 0, bar);
+                        tma_load_3d(dst + I8_A_BYTES, &tmB, static_cast<int>(ks * I8_BK), rb, 0, bar);
+                        if (++stage == I8_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            std::uint32_t stage = 0, phase = 0, unit_iter = 0;
+            for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
+                for (int h = 0; h < 2; ++h, ++unit_iter) {
+                    mbar_wait(tempty, (unit_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous unit
+                    tcgen05_fence_after();
+                    for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
+                        mbar_wait(full0 + 8 * stage, phase);
+                        tcgen05_fence_after();
+                        const std::uint32_t base = smem_u32(stages + stage * I8_STAGE_BYTES);
+                        const std::uint64_t d_a = umma_desc_sw64(base), d_b = umma_desc_sw64(base + I8_A_BYTES);
+                        #pragma unroll
+                        for (std::uint32_t k = 0; k < I8_BK / 32; ++k) {
+                            const std::uint64_t koff = static_cast<std::uint64_t>((k * 32) >> 4);  // 32 bytes per K = 32 step inside the swizzle atom
+                            const bool first = (ks | k) == 0u;
+                            // slice A_p times the slices B_q, q = S-1-p .. S-1, lands in the accumulators t' = 0 .. p (N <= 256 per instruction)
+                            #pragma unroll
+                            for (int pp = I8_S - 1; pp >= 0; --pp) {
+                                const int q_lo = I8_S - 1 - pp, cnt = pp + 1;
+                                #pragma unroll
+                                for (int c = 0; 4 * c < cnt; ++c) {
+                                    const int nsl = cnt - 4 * c < 4 ? cnt - 4 * c : 4;
+                                    umma_i8(tmem_base + static_cast<std::uint32_t>(c * 4 * I8_NH), d_a + koff + static_cast<std::uint64_t>((pp * I8_A_SLICE) >> 4),
+                                            d_b + koff + static_cast<std::uint64_t>(((q_lo + 4 * c) * I8_B_SLICE) >> 4), i8_idesc(static_cast<std::uint32_t>(nsl * I8_NH)),
+                                            (first && pp == I8_S - 1) ? 0u : 1u);
+                                }
+                            }
+                        }
+                        umma_commit(empty0 + 8 * stage);  // smem stage reusable once these MMAs have read it
+                        if (++stage == I8_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
+                    }
+                    umma_commit(tfull);  // all S accumulators of this unit complete
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns 32 ch .. + 31 of the unit =====
+        const int quarter = warp & 3;
+        const int ch = (warp - 2) >> 2;        // column half of the unit
+        const int row = quarter * 32 + lane;   // accumulator row of this thread
+        const int et = tid - 64;               // 0..255 among the epilogue threads
+        std::uint32_t unit_iter = 0;
+        for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
+            std::uint32_t I, J;
+            if constexpr (MODE == MODE_SYM) {
+                tri_decode(p.T_rows, L, I, J);
+            } else {
+                rect_decode(p.T_rows, p.T_cols, L, I, J);
+            }
+            const std::uint32_t row0 = I * TILE;
+            const bool diag = (MODE == MODE_SYM) && (I == J);
+            const double qa = (MODE == MODE_SYM) ? *p.QA_cost : 0.0;
+            double rowacc = 0.0;
+            for (int h = 0; h < 2; ++h, ++unit_iter) {
+                const std::uint32_t col0 = J * TILE + h * I8_NH;
+                if (h == 0 && et < TILE) {
+                    const std::uint32_t gi = row0 + et;
+                    const bool oki = gi < p.n_rows;
+                    s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : 0.0;
+                    s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : 0.0;
+                    s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : 0.0;
+                    s_row[3 * TILE + et] = oki ? p.A_scale[gi] : 0.0;
+                }
+                if (et >= TILE && et < TILE + I8_NH) {
+                    const int c = et - TILE;
+                    const std::uint32_t gj = col0 + c;
+                    const bool okj = gj < p.n_cols;
+                    s_col[0 * I8_NH + c] = (MODE == MODE_SYM && okj) ? p.q[gj] : 0.0;
+                    s_col[1 * I8_NH + c] = okj ? p.v[gj] : 0.0;
+                    s_col[2 * I8_NH + c] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : 0.0;
+                    s_col[3 * I8_NH + c] = okj ? p.B_scale[gj] : 0.0;
+                }
+                named_bar_sync(1, I8_EPI_THREADS);
+                const double qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row], sci = s_row[3 * TILE + row];
+
+                mbar_wait(tfull, unit_iter & 1u);
+                tcgen05_fence_after();
+                const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * 32);
+
+                // phase 1: S int32 diagonals -> one fp64 value per element (Horner from the least significant diagonal)
+                double a[32];
+                #pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    std::uint32_t r[I8_S][8];
+                    #pragma unroll
+                    for (int t = 0; t < I8_S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * I8_NH + g * 8), r[t]); }
+                    tmem_ld_wait();
+                    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        double s = i32_to_f64(r[0][j]);
+                        #pragma unroll
+                        for (int t = 1; t < I8_S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
+                        a[g * 8 + j] = s;
+                    }
+                }
+                // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(tempty); }
+
+                // phase 2: kernel function and the weighted sums
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int cl = ch * 32 + j;
+                    const double dot = a[j] * (sci * s_col[3 * I8_NH + cl]);
+                    const double kv = kernel_from_dot<KERNEL>(dot, sqi, s_col[2 * I8_NH + cl], p.kp);
+                    double t = kv;
+                    if constexpr (MODE == MODE_SYM) {
+                        t = kv + qa - qi - s_col[0 * I8_NH + cl];
+                        if (diag && row == h * I8_NH + cl) { t += p.cost_inv; }
+                    }
+                    rowacc = fma(t, s_col[1 * I8_NH + cl], rowacc);
+                    a[j] = t * vi;  // mirrored contribution of this row to column cl
+                }
+                if constexpr (MODE == MODE_SYM) {
+                    if (!diag) {  // CTA-uniform
+                        // butterfly: after 5 halving steps lane c holds the sum over the warp's 32 rows of column ch * 32 + c
+                        #pragma unroll
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            const bool upper = (lane & step) != 0;
+                            #pragma unroll
+                            for (int k = 0; k < step; ++k) {
+                                const double send = upper ? a[k] : a[k + step];
+                                const double keep = upper ? a[k + step] : a[k];
+                                a[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                            }
+                        }
+                        s_colsum[quarter * I8_NH + ch * 32 + lane] = a[0];
+                    }
+                }
+                if (h == 1 && ch == 1) { s_rowsum[row] = rowacc; }
+                named_bar_sync(1, I8_EPI_THREADS);  // column sums of the four row quarters / row sums of the second column half visible
+                if constexpr (MODE == MODE_SYM) {
+                    if (!diag && et < I8_NH) {
+                        const double s = ((s_colsum[et] + s_colsum[I8_NH + et]) + s_colsum[2 * I8_NH + et]) + s_colsum[3 * I8_NH + et];
+                        const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
+                        p.partial[mslot * TILE + h * I8_NH + et] = (col0 + et < p.n_cols) ? s : 0.0;
+                    }
+                }
+                if (h == 1 && ch == 0) {
+                    const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
+                    p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : 0.0;
+                }
+                named_bar_sync(1, I8_EPI_THREADS);  // s_col / s_colsum / s_rowsum consumed before the next unit overwrites them
+            }
+        }
+    }
+
+    // teardown: everyone done with TMEM before the allocating warp frees it
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace pb

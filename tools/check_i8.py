@@ -1,0 +1,87 @@
+"""Hardware check of the fp64 int8-slice tensor path (tcgen05 kind::i8, tile_i8.cuh) against the DMMA tiles and the oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle  # noqa: E402
+import plssvm_b200 as pb  # noqa: E402
+from datagen import make_data  # noqa: E402
+
+be = pb.Backend(0)
+orc = oracle.Oracle("reference" if oracle.available("reference") else "port")
+quick = "--quick" in sys.argv
+worst = 0.0
+for (N, d) in ((2, 3), (130, 1), (130, 40), (300, 64), (386, 65), (1000, 96), (2049, 333), (700, 1200)):
+    for kernel, kid in (("linear", 0), ("polynomial", 1), ("rbf", 2)):
+        X, y = make_data(N, d, 7, np.float64)
+        if N > 100:  # rows of very different magnitude exercise the per-row scaling
+            X[3] *= 1e-6
+            X[5] *= 300.0
+            X[7, ::2] *= 1e-9
+        n = N - 1
+        ds = be.dataset(X)
+        q, k_last = be.run_q_kernel(ds, kernel)
+        v = np.random.default_rng(3).uniform(1, 2, n)
+        outs = {}
+        for impl in (2, 6):
+            be.set_option("impl", impl)
+            outs[impl] = be.run_svm_kernel(ds, q, v, np.zeros_like(v), k_last + 1.0, 1.0, 1.0, kernel)
+        be.set_option("impl", 0)
+        want = orc.matvec(kid, X, q, v, np.zeros(n), float(k_last) + 1.0, 1.0, 1.0, gamma=1.0 / d)
+        sc = np.max(np.abs(want))
+        e2 = np.max(np.abs(outs[2] - want)) / sc
+        e6 = np.max(np.abs(outs[6] - want)) / sc
+        worst = max(worst, e6)
+        print(f"N={N:5d} d={d:4d} {kernel:10s} dmma {e2:.2e}  i8 {e6:.2e}  (vs fp64 oracle)", flush=True)
+print("worst i8 matvec error:", worst, "OK" if worst < 1e-12 else "FAIL", flush=True)
+
+# predict (rectangular tiles)
+X, y = make_data(3000, 200, 11, np.float64)
+ds = be.dataset(X)
+P, _ = make_data(700, 200, 10, np.float64)
+alpha = np.random.default_rng(5).standard_normal(3000)
+for kernel in ("polynomial", "rbf"):
+    vals = {}
+    for impl in (2, 6):
+        be.set_option("impl", impl)
+        vals[impl], _ = be.predict_values(ds, alpha, 0.1, be.dataset(P), kernel)
+        vals[(impl, "host")], _ = be.predict_values(X, alpha, 0.1, P, kernel)
+    sc = np.max(np.abs(vals[2]))
+    print(f"predict {kernel}: |i8 - dmma| / scale = {np.max(np.abs(vals[6] - vals[2])) / sc:.2e}   host-staged: {np.max(np.abs(vals[(6, 'host')] - vals[2])) / sc:.2e}", flush=True)
+be.set_option("impl", 0)
+
+# full solve parity between the two tile kernels
+X, y = make_data(1500, 128, 21, np.float64)
+res = {}
+for impl in (2, 6):
+    be.set_option("impl", impl)
+    res[impl] = be.solve(X, y, "rbf", eps=1e-10)
+a2, a6 = res[2]["alpha"], res[6]["alpha"]
+print("solve rbf 1500x128: iterations", res[2]["iterations"], res[6]["iterations"], " alpha rel diff", float(np.max(np.abs(a2 - a6)) / np.max(np.abs(a2))), " rho", res[2]["rho"],
+      res[6]["rho"], flush=True)
+be.set_option("impl", 0)
+
+# timing
+for (N, d, kernel) in ((16385, 4096, "rbf"),) if quick else ((16385, 4096, "rbf"), (32769, 4096, "rbf"), (32769, 1024, "polynomial"), (32769, 2048, "linear")):
+    X, y = make_data(N, d, 9, np.float64)
+    ds = be.dataset(X)
+    q, k_last = be.run_q_kernel(ds, kernel)
+    v = np.ones(N - 1)
+    for impl in (2, 6):
+        be.set_option("impl", impl)
+        ts = []
+        for _ in range(4):
+            out = be.run_svm_kernel(ds, q, v, np.zeros_like(v), k_last + 1.0, 1.0, 1.0, kernel)
+            t = be.timings()
+            ts.append(t["matvec_tile_ms"])
+        print(f"{N}x{d} {kernel} impl {impl}: tile kernel {min(ts):.3f} ms -> {t['matvec_flops'] / min(ts) / 1e9:.1f} TFLOP/s (fp64-equivalent)  all: {[round(x, 3) for x in ts]}", flush=True)
+        if impl == 2:
+            ref = out
+        else:
+            print("   |i8 - dmma| / scale =", float(np.max(np.abs(out - ref)) / np.max(np.abs(ref))), flush=True)
+    be.set_option("impl", 0)
+    del ds
