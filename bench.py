@@ -49,7 +49,8 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the number of data points (development only; marks the line as non-headline)")
     ap.add_argument("--features", type=int, default=0, help="override the number of features (development only)")
-    ap.add_argument("--tile-impl", type=int, default=0, help="0 auto, 1 SIMT tiles, 2 tensor-core tiles")
+    ap.add_argument("--tile-impl", type=int, default=0, help="0 auto (fp64: int8 slices on tcgen05, fp32: tcgen05 3xTF32), 1 SIMT tiles, 2 fp64 DMMA / fp32 3xTF32 tiles, 6 fp64 int8-slice tiles")
+    ap.add_argument("--no-dmma-line", action="store_true", help="fp64 only: skip the short extra run of the native-FP64 DMMA tiles reported under 'fp64_dmma_tiles'")
     ap.add_argument("--linear-factorized", action="store_true", help="linear kernel only: time the factorised X (X^T v) matvec (HBM-bound) instead of the implicit tiles")
     ap.add_argument("--full-solve", action="store_true", help="additionally run the whole fit to eps = 1e-8 (fp64) / 1e-4 (fp32) through the C ABI; with C1 also on the CPU reference")
     ap.add_argument("--no-e2e", action="store_true")
@@ -310,20 +311,33 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (the tile kernel) ---------------------------------------------------------------------------
     peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
     peak, peak_src = 37.0, "vendor figure (fallback: profiles/peaks_b200.json missing)"
-    tensor = t_after["impl_used"] == 2
+    impl_used = t_after["impl_used"]
+    tensor = impl_used in (2, 6)
     key = "dmma_tflops_sustained_3s" if dtype == "float64" else ("cublas_sgemm_tf32_random_tflops_sustained_4s" if tensor else "ffma_tflops")
-    if os.path.exists(peaks_path):
-        pk = json.load(open(peaks_path))
-        if key in pk:
-            peak, peak_src = float(pk[key]), f"measured on this pool's B200 by tools/peak_probe ({key}; profiles/peaks_b200.json)"
-            if dtype != "float64" and tensor:  # 3xTF32: three TF32 MMAs per algorithmic fp32 product
-                peak, peak_src = peak / 3.0, peak_src + " / 3 (3xTF32 split)"
+    pk = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+    if key in pk:
+        peak, peak_src = float(pk[key]), f"measured on this pool's B200 by tools/peak_probe ({key}; profiles/peaks_b200.json)"
+        if dtype != "float64" and tensor:  # 3xTF32: three TF32 MMAs per algorithmic fp32 product
+            peak, peak_src = peak / 3.0, peak_src + " / 3 (3xTF32 split)"
+    fp64_pipe_peak = peak if dtype == "float64" else None
+    if impl_used == 6:
+        # int8-slice tiles: 28 int8 tensor-core MACs per algorithmic fp64 MAC (S = 7 slices, digit diagonals p + q >= 6), so the roofline of
+        # this kernel is the int8 tensor pipe / 28: tcgen05.mma kind::i8 issue-loop peak with random operands, measured by tools/i8_peak_probe
+        # (burst when the kernel is timed alone, the sustained figure inside a long step; profiles/r01/i8_peaks_b200.json)
+        i8_path = os.path.join(ROOT, "profiles", "r01", "i8_peaks_b200.json")
+        i8 = json.load(open(i8_path)) if os.path.exists(i8_path) else {}
+        long_step = args.steps * (dev_ms / max(args.steps, 1)) > 2000.0
+        k8 = "i8_mma_n256_random_tops_sustained_3s" if long_step else "i8_mma_n256_random_tops_burst"
+        peak = float(i8.get(k8, 4500.0)) / 28.0
+        peak_src = (f"int8 tensor pipe / 28 products per fp64 product: tcgen05.mma kind::i8 issue-loop peak, random operands ({k8} = {i8.get(k8, 'nominal 4500')} TOPS, "
+                    "measured on this pool's B200 by tools/i8_peak_probe; profiles/r01/i8_peaks_b200.json)")
     avg_tile_s = tile_ms / max(tile_calls, 1) * 1e-3
     achieved = (F / world) / avg_tile_s / 1e12 if avg_tile_s > 0 else 0.0
-    traffic = None
+    traffic, traffic_i8 = None, None
     ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(ncu_path):
         traffic = json.load(open(ncu_path)).get(args.workload)
+        traffic_i8 = json.load(open(ncu_path)).get(args.workload + "_i8")
     if t_after["impl_used"] == 3:
         # factorised linear matvec: HBM-bound, 2 passes over X per matvec; report bytes/s of the whole matvec against the copy bandwidth
         mv_s = (t_after["matvec_ms"] - t_before["matvec_ms"]) / max(tile_calls, 1) * 1e-3
@@ -335,9 +349,35 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": ("tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)") + f"<{kernel}, sym>" if tensor else "tile_kernel_simt", "peak_source": peak_src,
+    kname = {6: "tile_kernel_i8 (fp64 through int8 slices, tcgen05 kind::i8)", 2: "tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)"}.get(impl_used)
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic if impl_used == 2 else None,
+                "kernel": kname + f"<{kernel}, sym>" if tensor else "tile_kernel_simt", "peak_source": peak_src,
                 "avg_launch_ms": avg_tile_s * 1e3, "launches_timed": int(tile_calls), "flops_per_launch": F / world}
+    if impl_used == 6:
+        roofline["int8_tops"] = achieved * 28.0
+        roofline["vs_fp64_pipe_peak"] = achieved / fp64_pipe_peak  # > 1: the fp64-accurate result is produced faster than the FP64 pipes (DMMA = DFMA) can run
+        roofline["fp64_pipe_peak_tflops"] = fp64_pipe_peak
+        if traffic_i8 is not None:
+            roofline["traffic"] = traffic_i8
+
+    # fp64: the native-FP64 DMMA tiles (north-star kernel, tile_dmma.cuh) on the same resident data, a few iterations, against the DMMA peak
+    dmma_line = None
+    if dtype == "float64" and impl_used == 6 and world == 1 and not args.no_dmma_line:
+        be.set_option("impl", 2)
+        be.set_option("ignore_convergence", 1)
+        cg2 = be.cg_begin(ds, y_host, kernel, eps=eps)
+        cg2.step(1)
+        tb = be.timings()
+        cg2.step(3)
+        ta = be.timings()
+        cg2.finish()
+        be.set_option("ignore_convergence", 0)
+        be.set_option("impl", args.tile_impl)
+        ms2 = (ta["matvec_tile_ms"] - tb["matvec_tile_ms"]) / max(ta["matvec_calls"] - tb["matvec_calls"], 1)
+        a2 = (F / world) / (ms2 * 1e-3) / 1e12
+        dmma_line = {"kernel": f"tile_kernel_dmma<{kernel}, sym>", "avg_launch_ms": ms2, "achieved": a2, "peak": fp64_pipe_peak, "unit": "TFLOP/s", "frac": a2 / fp64_pipe_peak,
+                     "traffic": traffic, "launches_timed": int(ta["matvec_calls"] - tb["matvec_calls"]),
+                     "note": "the same matvec with --tile-impl 2: TMA + mma.sync m8n8k4.f64 tiles against the measured DMMA issue peak"}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -375,8 +415,9 @@ def run_ours(args):
         "cg_iters_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "final_residual": float(res["delta"]), "tile_impl": int(t_after["impl_used"]), "full_solve": full,
-        "precision_note": None if dtype == "float64" else "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)",
-        "matvecs_in_timed_region": int(tile_calls), "reference_cuda_baseline": ref_cuda,
+        "precision_note": ("fp64 storage, vectors and epilogue; x_i.x_j through 7 int8 digit planes per operand, 28 exact int32 tensor-core products recombined in fp64 "
+                           "(error vs the fp64 oracle <= that of the DMMA tiles)" if impl_used == 6 else None) if dtype == "float64" else "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)",
+        "matvecs_in_timed_region": int(tile_calls), "reference_cuda_baseline": ref_cuda, "fp64_dmma_tiles": dmma_line,
     }
     print(json.dumps(_finite(line)), flush=True)
     if world > 1:
@@ -410,6 +451,8 @@ def run_predict(args):
     m = PREDICT_STEP_POINTS  # per rank and step: test points are independent units, sharded over ranks with no collective
     F = 2.0 * m * n_sv * d
     be = pb.Backend(local_rank)
+    if args.tile_impl:
+        be.set_option("impl", args.tile_impl)
     SV, _ = make_device_data(n_sv, d, dtype, 47, device)
     P, _ = make_device_data(m, d, dtype, 48 + rank, device)
     rng = np.random.default_rng(47)
@@ -454,7 +497,15 @@ def run_predict(args):
             dist.destroy_process_group()
         return
     peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
-    peak = float(json.load(open(peaks_path)).get("dmma_tflops_sustained_3s", 37.0)) if os.path.exists(peaks_path) else 37.0
+    fp64_pipe_peak = float(json.load(open(peaks_path)).get("dmma_tflops_sustained_3s", 37.0)) if os.path.exists(peaks_path) else 37.0
+    impl_used = t["impl_used"]
+    peak, kname, peak_src = fp64_pipe_peak, "tile_kernel_dmma<rbf, rect>", "measured DMMA issue peak (profiles/peaks_b200.json)"
+    if impl_used == 6:  # int8-slice tiles: int8 tensor pipe / 28 (see run_ours)
+        i8_path = os.path.join(ROOT, "profiles", "r01", "i8_peaks_b200.json")
+        i8 = json.load(open(i8_path)) if os.path.exists(i8_path) else {}
+        k8 = "i8_mma_n256_random_tops_sustained_3s" if wall > 2.0 else "i8_mma_n256_random_tops_burst"
+        peak = float(i8.get(k8, 4500.0)) / 28.0
+        kname, peak_src = "tile_kernel_i8<rbf, rect> (fp64 through int8 slices, tcgen05 kind::i8)", f"int8 tensor pipe / 28: {k8} (tools/i8_peak_probe; profiles/r01/i8_peaks_b200.json)"
     achieved = F * args.steps / (tile_ms * 1e-3) / 1e12 if tile_ms > 0 else 0.0
     line = {
         "metric": "predict_tflops", "value": world * F * args.steps / wall / 1e12, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -463,8 +514,9 @@ def run_predict(args):
                    "l2": "points (2.1 GB) and support vectors (2.1 GB) larger than L2"},
         "points_per_s": world * m * args.steps / wall, "seconds_for_1048576_points": 1048576.0 / (world * m * args.steps / wall),
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": "tile_kernel_dmma<rbf, rect>"},
-        "cpu_baseline": None,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": kname, "peak_source": peak_src,
+                     "vs_fp64_pipe_peak": achieved / fp64_pipe_peak},
+        "cpu_baseline": None, "tile_impl": int(impl_used),
     }
     print(json.dumps(_finite(line)), flush=True)
     if world > 1:

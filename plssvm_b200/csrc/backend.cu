@@ -208,6 +208,7 @@ struct plssvm_b200_dataset {
     // fp64 only, created on first use by the int8-slice tensor path (impl 6): digit planes [I8_S][N][ld8] and row scales
     void *X_i8 = nullptr, *rscale = nullptr;
     std::size_t ld8 = 0;
+    int i8_bad_rows = 0;  // rows whose elements are spread over too many orders of magnitude for the automatic choice (split_i8_kernel)
 };
 
 namespace {
@@ -277,9 +278,9 @@ inline std::size_t pitch_i8(const std::size_t d) { return (d + 127) / 128 * 128;
 
 // fp64 rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold I8_S * rows * ld8 bytes
 void run_split_i8(plssvm_b200_ctx *ctx, const double *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8,
-                  double *rscale, cudaStream_t st) {
+                  double *rscale, int *bad_rows, cudaStream_t st) {
     pb::split_i8_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(X, rows, static_cast<std::uint32_t>(d), static_cast<std::uint32_t>(ld), planes, rows * ld8,
-                                                                              static_cast<std::uint32_t>(ld8), rscale);
+                                                                              static_cast<std::uint32_t>(ld8), rscale, bad_rows);
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
 }
@@ -289,9 +290,18 @@ void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
     if (ds->X_i8 != nullptr) { return; }
     ds->ld8 = pitch_i8(ds->d);
     PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(pb::I8_S) * ds->N * ds->ld8));
-    PB_CUDA(cudaMalloc(&ds->rscale, ds->N * sizeof(double)));
-    run_split_i8(ctx, static_cast<const double *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<double *>(ds->rscale), ctx->stream);
+    PB_CUDA(cudaMalloc(&ds->rscale, (ds->N + 1) * sizeof(double)));
+    int *range_d = reinterpret_cast<int *>(static_cast<double *>(ds->rscale) + ds->N);  // scratch word behind the scales
+    PB_CUDA(cudaMemsetAsync(range_d, 0, sizeof(int), ctx->stream));
+    run_split_i8(ctx, static_cast<const double *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<double *>(ds->rscale), range_d, ctx->stream);
+    int *h = static_cast<int *>(ctx->pinned) + 512;  // second half of the pinned block (the first holds the CG state read-back)
+    PB_CUDA(cudaMemcpyAsync(h, range_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ds->i8_bad_rows = *h;
 }
+
+// automatic kernel choice only: the int8-slice tiles are used unless the data set holds badly scaled rows (split_i8_kernel)
+bool i8_allowed(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds) { return ctx->impl == 6 || ds->i8_bad_rows == 0; }
 
 template <typename T, int KERNEL, int MODE>
 void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
@@ -364,12 +374,14 @@ int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
     if (ctx->impl == 6) { return (sizeof(T) == 8 && features <= pb::I8_MAX_FEATURES) ? 6 : 2; }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
-    return 2;  // tensor-core tiles: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
+    // auto: fp64 -> int8 slices on tcgen05 (tile_i8.cuh) where the accumulators cannot overflow (callers fall back to 2 = TMA + DMMA,
+    // tile_dmma.cuh, for badly scaled rows: i8_allowed); fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
+    if (sizeof(T) == 8 && features > 0 && features <= pb::I8_MAX_FEATURES) { return 6; }
+    return 2;
 }
 
 template <typename T, int MODE>
-void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p) {
-    const int impl = resolve_impl<T>(ctx, p.ld);
+void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
     ctx->tm.impl_used = impl;
     switch (p.kp.kernel) {
         case pb::K_LINEAR: launch_tiles_t<T, pb::K_LINEAR, MODE>(ctx, p, impl); break;
@@ -398,6 +410,7 @@ struct matvec_plan {
     std::uint32_t n;  // N - 1
     std::uint32_t Tb; // tiles per side
     int tile_shift = 0;
+    int impl = 2;
     std::uint64_t tile_lo, tile_hi;
     dbuf<T> partial;
     TileParams<T> base;
@@ -406,18 +419,24 @@ struct matvec_plan {
         ctx(c), ds(data) {
         n = static_cast<std::uint32_t>(data->N - 1);
         Tb = (n + TILE - 1) / TILE;
-        const int impl = resolve_impl<T>(c, data->ld);
+        const bool tiles_needed = !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR);
+        impl = resolve_impl<T>(c, data->ld);
+        if constexpr (sizeof(T) == 8) {
+            if (impl == 6 && tiles_needed) {
+                ensure_i8(c, const_cast<plssvm_b200_dataset *>(data));
+                if (!i8_allowed(c, data)) { impl = 2; }
+            }
+        }
         tile_shift = (impl == 4 || impl == 5) ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
         pb::rank_range(pb::tri_num_tiles((Tb + tile_shift) >> tile_shift), c->rank, c->world, tile_lo, tile_hi);
-        if (!(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
+        if (tiles_needed) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
         base.A = static_cast<const T *>(data->X);
         base.B = base.A;
         base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
         base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
         if constexpr (sizeof(T) == 8) {
-            if (impl == 6 && !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR)) {
-                ensure_i8(c, const_cast<plssvm_b200_dataset *>(data));
+            if (impl == 6 && tiles_needed) {
                 base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
                 base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
                 base.A_plane = base.B_plane = data->N * data->ld8;
@@ -476,7 +495,7 @@ struct matvec_plan {
         p.v = v;
         const bool timed_mv = ctx->matvec_timer.begin(ctx->stream);
         const bool timed = ctx->tile_timer.begin(ctx->stream);
-        launch_tiles<T, pb::MODE_SYM>(ctx, p);
+        launch_tiles<T, pb::MODE_SYM>(ctx, p, impl);
         if (timed) { ctx->tile_timer.end(ctx->stream); }
         pb::reduce_partials_kernel<T, pb::MODE_SYM><<<Tb, 512, 0, ctx->stream>>>(partial.p, out, n, Tb, Tb, tile_lo, tile_hi, ctx->world > 1 ? 1 : 0, tile_shift, T(1), T(0), 0, base.done);
         PB_CUDA(cudaGetLastError());
@@ -758,7 +777,8 @@ void run_w_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *
 // points: `pts` rows [p0, p0 + m) of a resident matrix; out_d: m values on the device
 template <typename T>
 void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, const T *w_d, const T rho, const T *P, const T *P_sq, const T *P_hi,
-                         const T *P_lo, const std::int8_t *P_i8, const T *P_scale, const std::size_t P_plane, const std::size_t m, const KernelParams<T> &kp, T *out_d) {
+                         const T *P_lo, const std::int8_t *P_i8, const T *P_scale, const std::size_t P_plane, const std::size_t m, const KernelParams<T> &kp, const int impl,
+                         T *out_d) {
     const std::uint32_t ld = static_cast<std::uint32_t>(sv->ld);
     if (kp.kernel == pb::K_LINEAR) {
         pb::linear_predict_kernel<T><<<static_cast<unsigned>((m + 7) / 8), 256, 0, ctx->stream>>>(P, m, ld, w_d, rho, out_d);
@@ -780,12 +800,10 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.T_cols = (p.n_cols + TILE - 1) / TILE;
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
-    const int impl = resolve_impl<T>(ctx, ld);
     if (impl == 4 || impl == 5) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
     if constexpr (sizeof(T) == 8) {
         if (impl == 6) {
             PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
-            ensure_i8(ctx, const_cast<plssvm_b200_dataset *>(sv));
             p.A_i8 = P_i8;
             p.A_scale = P_scale;
             p.A_plane = P_plane;
@@ -801,7 +819,7 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.kp = kp;
     p.partial = workspace<T>(ctx, plssvm_b200_ctx::WS_PARTIAL, static_cast<std::size_t>(p.T_rows) * p.T_cols * TILE);
     const bool timed = ctx->tile_timer.begin(ctx->stream);
-    launch_tiles<T, pb::MODE_RECT>(ctx, p);
+    launch_tiles<T, pb::MODE_RECT>(ctx, p, impl);
     if (timed) { ctx->tile_timer.end(ctx->stream); }
     pb::reduce_partials_kernel<T, pb::MODE_RECT><<<p.T_rows, 512, 0, ctx->stream>>>(p.partial, out_d, p.n_rows, p.T_rows, p.T_cols, 0, p.tile_hi, 0, 0, T(1), -rho, 0, nullptr);
     PB_CUDA(cudaGetLastError());
@@ -855,13 +873,18 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
     const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx) >= 2;  // every tcgen05 variant (impl 2, 4, 5) consumes the hi / lo split
-    const bool need_i8 = sizeof(T) == 8 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx, sv->ld) == 6;  // int8 digit planes of the points (tile_i8.cuh)
+    int impl = resolve_impl<T>(ctx, sv->ld);
+    if constexpr (sizeof(T) == 8) {
+        if (impl == 6 && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
+            ensure_i8(ctx, sv);
+            if (pts_ds != nullptr) { ensure_i8(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
+            if (!i8_allowed(ctx, sv) || (pts_ds != nullptr && !i8_allowed(ctx, pts_ds))) { impl = 2; }
+        }
+    }
+    const bool need_i8 = sizeof(T) == 8 && kernel != pb::K_LINEAR && impl == 6;
     const std::size_t ld8 = pitch_i8(sv->d);
     std::int8_t *stage_i8[2] = { nullptr, nullptr };
     T *stage_sc[2] = { nullptr, nullptr };
-    if (need_i8 && pts_ds != nullptr) {
-        if constexpr (sizeof(T) == 8) { ensure_i8(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
-    }
     if (pts_ds == nullptr) {
         const int n_stage = m > PREDICT_BATCH ? 2 : 1;
         for (int i = 0; i < n_stage; ++i) {
@@ -927,7 +950,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                 }
                 if constexpr (sizeof(T) == 8) {
                     if (need_i8) {
-                        run_split_i8(ctx, stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], st);
+                        run_split_i8(ctx, stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], nullptr, st);
                         P_i8 = stage_i8[buf];
                         P_scale = stage_sc[buf];
                         P_plane = mb * ld8;
@@ -938,7 +961,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                 P_hi = stage_hi[buf];
                 P_lo = stage_lo[buf];
             }
-            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, P_i8, P_scale, P_plane, mb, kp, out_d + (p0 - s0));
+            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, P_i8, P_scale, P_plane, mb, kp, impl, out_d + (p0 - s0));
             if (pts_ds == nullptr) { PB_CUDA(cudaEventRecord(ctx->ev_computed[batch_index & 1], st)); }
         }
         PB_CUDA(cudaMemcpyAsync(out + s0, out_d, ms * sizeof(T), cudaMemcpyDeviceToHost, st));

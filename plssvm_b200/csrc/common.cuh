@@ -86,7 +86,7 @@ __device__ __forceinline__ T kernel_from_dot(const T dot, const T sq_i, const T 
         return ipow(pb_fma(kp.gamma, dot, kp.coef0), kp.degree);
     } else {
         T d2 = pb_fma(T(-2), dot, sq_i + sq_j);
-        d2 = d2 > T(0) ? d2 : T(0);
+        d2 = d2 < T(0) ? T(0) : d2;  // (a NaN distance stays NaN)
         return pb_exp(-kp.gamma * d2);
     }
 }

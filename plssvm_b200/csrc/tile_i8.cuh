@@ -48,33 +48,55 @@ constexpr int I8_VEC_BYTES = (4 * TILE + 4 * I8_NH + 4 * I8_NH + TILE) * 8;  // 
 constexpr int I8_SMEM_BYTES = 1024 + I8_STAGES * I8_STAGE_BYTES + I8_VEC_BYTES + (2 * I8_STAGES + 2) * 8 + 16;
 constexpr std::uint32_t I8_TMEM_COLS = 512;
 constexpr std::uint32_t I8_MAX_FEATURES = 16384;           // 7 products of <= 2^14 per feature and diagonal stay below 2^31
+constexpr int I8_AUTO_MAX_RANGE = 20;                      // automatic choice: see split_i8_kernel (badly scaled rows -> DMMA tiles)
 
 static_assert(I8_S * I8_NH <= 512, "accumulators must fit into TMEM");
 static_assert(I8_STAGE_BYTES % 1024 == 0, "stage alignment");
 
 // ---- operand preparation: fp64 rows -> S int8 digit planes + per-row scale ------------------------------------------------
-// planes[p][row][k] (row pitch ld8 bytes, zero padded), rscale[row] = 2^(e_row - 6); one warp per row
+// planes[p][row][k] (row pitch ld8 bytes, zero padded), rscale[row] = 2^(e_row - 6); one warp per row.
+// The products are accurate to ~2^-54 sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
+// which is at most the row norm), but elements far below their row's maximum keep fewer significant bits of their own.
+// bad_rows (optional) counts the rows where more than 1 / 16 of the non-zero elements lie more than 2^I8_AUTO_MAX_RANGE below the
+// largest one; the automatic kernel choice falls back to the DMMA tiles for such badly scaled data.
+// Rows containing inf / NaN get a NaN scale, so they poison their results exactly like native fp64 arithmetic would.
 __global__ void __launch_bounds__(256) split_i8_kernel(const double *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
                                                        std::int8_t *__restrict__ planes, const std::size_t plane_stride, const std::uint32_t ld8,
-                                                       double *__restrict__ rscale) {
+                                                       double *__restrict__ rscale, int *__restrict__ bad_rows) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) { return; }
     const int lane = threadIdx.x & 31;
     const double *x = X + row * ld;
-    double mx = 0.0;
-    for (std::uint32_t k = lane; k < d; k += 32) { mx = fmax(mx, fabs(x[k])); }
+    double mx = 0.0, poison = 0.0;
+    for (std::uint32_t k = lane; k < d; k += 32) {
+        const double ax = fabs(x[k]);
+        mx = fmax(mx, ax);
+        poison += ax * 0.0;  // NaN iff the row holds an inf or a NaN
+    }
     #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        poison += __shfl_xor_sync(0xffffffffu, poison, o);
+    }
+    const bool bad = poison != 0.0 || mx > 1.0e300;  // (poison is 0 or NaN)
+    if (bad) { mx = 0.0; }
     int e = 0;
     if (mx > 0.0) { (void) frexp(mx, &e); }  // mx = m 2^e, m in [0.5, 1)  =>  |x_k| < 2^e
     e = e < -900 ? -900 : e;
-    const double to_fixed = ldexp(1.0, (8 * I8_S - 2) - e);
-    if (lane == 0) { rscale[row] = ldexp(1.0, e - 6); }
+    const double to_fixed = bad ? 0.0 : ldexp(1.0, (8 * I8_S - 2) - e);
+    const double small = ldexp(1.0, e - I8_AUTO_MAX_RANGE);
+    if (lane == 0) { rscale[row] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, e - 6); }
     std::int8_t *out = planes + row * ld8;
+    unsigned n_nonzero = 0, n_small = 0;
     for (std::uint32_t k0 = 4u * lane; k0 < ld8; k0 += 128u) {
         long long v[4];
         #pragma unroll
-        for (int j = 0; j < 4; ++j) { v[j] = (k0 + j < d) ? __double2ll_rn(x[k0 + j] * to_fixed) : 0ll; }
+        for (int j = 0; j < 4; ++j) {
+            const double xv = (k0 + j < d && !bad) ? x[k0 + j] : 0.0;
+            n_nonzero += xv != 0.0 ? 1u : 0u;
+            n_small += (xv != 0.0 && fabs(xv) < small) ? 1u : 0u;
+            v[j] = __double2ll_rn(xv * to_fixed);
+        }
         #pragma unroll
         for (int p = 0; p < I8_S; ++p) {
             std::uint32_t word = 0;
@@ -86,6 +108,14 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double *__restrict_
             }
             *reinterpret_cast<std::uint32_t *>(out + static_cast<std::size_t>(p) * plane_stride + k0) = word;
         }
+    }
+    if (bad_rows != nullptr) {
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_nonzero += __shfl_xor_sync(0xffffffffu, n_nonzero, o);
+            n_small += __shfl_xor_sync(0xffffffffu, n_small, o);
+        }
+        if (lane == 0 && 16u * n_small > n_nonzero) { atomicAdd(bad_rows, 1); }
     }
 }
 
