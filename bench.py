@@ -319,18 +319,19 @@ def run_ours(args):
         peak, peak_src = float(pk[key]), f"measured on this pool's B200 by tools/peak_probe ({key}; profiles/peaks_b200.json)"
         if dtype != "float64" and tensor:  # 3xTF32: three TF32 MMAs per algorithmic fp32 product
             peak, peak_src = peak / 3.0, peak_src + " / 3 (3xTF32 split)"
-    fp64_pipe_peak = peak if dtype == "float64" else None
+    fp_pipe_peak = peak  # fp64: DMMA issue peak; fp32: TF32 tensor peak / 3
+    i8_products = 28.0 if dtype == "float64" else 10.0
     if impl_used == 6:
-        # int8-slice tiles: 28 int8 tensor-core MACs per algorithmic fp64 MAC (S = 7 slices, digit diagonals p + q >= 6), so the roofline of
-        # this kernel is the int8 tensor pipe / 28: tcgen05.mma kind::i8 issue-loop peak with random operands, measured by tools/i8_peak_probe
-        # (burst when the kernel is timed alone, the sustained figure inside a long step; profiles/r01/i8_peaks_b200.json)
+        # int8-slice tiles: 28 (fp64: S = 7 slices, digit diagonals p + q >= 6) or 10 (fp32: S = 4) int8 tensor-core MACs per algorithmic MAC,
+        # so the roofline of this kernel is the int8 tensor pipe / 28 (/ 10): tcgen05.mma kind::i8 issue-loop peak with random operands, measured
+        # by tools/i8_peak_probe (burst when the kernel is timed alone, the sustained figure inside a long step; profiles/r01/i8_peaks_b200.json)
         i8_path = os.path.join(ROOT, "profiles", "r01", "i8_peaks_b200.json")
         i8 = json.load(open(i8_path)) if os.path.exists(i8_path) else {}
         long_step = args.steps * (dev_ms / max(args.steps, 1)) > 2000.0
         k8 = "i8_mma_n256_random_tops_sustained_3s" if long_step else "i8_mma_n256_random_tops_burst"
-        peak = float(i8.get(k8, 4500.0)) / 28.0
-        peak_src = (f"int8 tensor pipe / 28 products per fp64 product: tcgen05.mma kind::i8 issue-loop peak, random operands ({k8} = {i8.get(k8, 'nominal 4500')} TOPS, "
-                    "measured on this pool's B200 by tools/i8_peak_probe; profiles/r01/i8_peaks_b200.json)")
+        peak = float(i8.get(k8, 4500.0)) / i8_products
+        peak_src = (f"int8 tensor pipe / {int(i8_products)} int8 products per {'fp64' if dtype == 'float64' else 'fp32'} product: tcgen05.mma kind::i8 issue-loop peak, random operands "
+                    f"({k8} = {i8.get(k8, 'nominal 4500')} TOPS, measured on this pool's B200 by tools/i8_peak_probe; profiles/r01/i8_peaks_b200.json)")
     avg_tile_s = tile_ms / max(tile_calls, 1) * 1e-3
     achieved = (F / world) / avg_tile_s / 1e12 if avg_tile_s > 0 else 0.0
     traffic, traffic_i8 = None, None
@@ -349,14 +350,15 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    kname = {6: "tile_kernel_i8 (fp64 through int8 slices, tcgen05 kind::i8)", 2: "tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)"}.get(impl_used)
+    kname = {6: f"tile_kernel_i8 ({'fp64' if dtype == 'float64' else 'fp32'} through int8 slices, tcgen05 kind::i8)", 2: "tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)"}.get(impl_used)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic if impl_used == 2 else None,
                 "kernel": kname + f"<{kernel}, sym>" if tensor else "tile_kernel_simt", "peak_source": peak_src,
                 "avg_launch_ms": avg_tile_s * 1e3, "launches_timed": int(tile_calls), "flops_per_launch": F / world}
     if impl_used == 6:
-        roofline["int8_tops"] = achieved * 28.0
-        roofline["vs_fp64_pipe_peak"] = achieved / fp64_pipe_peak  # > 1: the fp64-accurate result is produced faster than the FP64 pipes (DMMA = DFMA) can run
-        roofline["fp64_pipe_peak_tflops"] = fp64_pipe_peak
+        roofline["int8_tops"] = achieved * i8_products
+        # > 1: the result is produced faster than the floating-point pipe of that precision could (fp64: DMMA = DFMA issue peak; fp32: TF32 tensor peak / 3)
+        roofline["vs_float_pipe_peak"] = achieved / fp_pipe_peak
+        roofline["float_pipe_peak_tflops"] = fp_pipe_peak
         if traffic_i8 is not None:
             roofline["traffic"] = traffic_i8
 
@@ -375,7 +377,7 @@ def run_ours(args):
         be.set_option("impl", args.tile_impl)
         ms2 = (ta["matvec_tile_ms"] - tb["matvec_tile_ms"]) / max(ta["matvec_calls"] - tb["matvec_calls"], 1)
         a2 = (F / world) / (ms2 * 1e-3) / 1e12
-        dmma_line = {"kernel": f"tile_kernel_dmma<{kernel}, sym>", "avg_launch_ms": ms2, "achieved": a2, "peak": fp64_pipe_peak, "unit": "TFLOP/s", "frac": a2 / fp64_pipe_peak,
+        dmma_line = {"kernel": f"tile_kernel_dmma<{kernel}, sym>", "avg_launch_ms": ms2, "achieved": a2, "peak": fp_pipe_peak, "unit": "TFLOP/s", "frac": a2 / fp_pipe_peak,
                      "traffic": traffic, "launches_timed": int(ta["matvec_calls"] - tb["matvec_calls"]),
                      "note": "the same matvec with --tile-impl 2: TMA + mma.sync m8n8k4.f64 tiles against the measured DMMA issue peak"}
 
@@ -415,8 +417,11 @@ def run_ours(args):
         "cg_iters_per_s": args.steps / (dev_ms * 1e-3), "wall_ms_per_step": wall / args.steps * 1e3,
         "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "final_residual": float(res["delta"]), "tile_impl": int(t_after["impl_used"]), "full_solve": full,
-        "precision_note": ("fp64 storage, vectors and epilogue; x_i.x_j through 7 int8 digit planes per operand, 28 exact int32 tensor-core products recombined in fp64 "
-                           "(error vs the fp64 oracle <= that of the DMMA tiles)" if impl_used == 6 else None) if dtype == "float64" else "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)",
+        "precision_note": (("fp64 storage, vectors and epilogue; x_i.x_j through 7 int8 digit planes per operand, 28 exact int32 tensor-core products recombined in fp64 "
+                            "(error vs the fp64 oracle <= that of the DMMA tiles)" if impl_used == 6 else None) if dtype == "float64" else
+                           ("fp32 storage, vectors and epilogue; x_i.x_j through 4 int8 digit planes per operand (30 bits), 10 exact int32 tensor-core products recombined in fp64, rounded "
+                            "once to fp32 (error vs the fp64 oracle ~2e-7, below the 3xTF32 tiles)" if impl_used == 6 else
+                            "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)")),
         "matvecs_in_timed_region": int(tile_calls), "reference_cuda_baseline": ref_cuda, "fp64_dmma_tiles": dmma_line,
     }
     print(json.dumps(_finite(line)), flush=True)

@@ -205,7 +205,7 @@ struct plssvm_b200_dataset {
     void *X = nullptr;   // [N][ld]
     void *sq = nullptr;  // [N]
     void *X_hi = nullptr, *X_lo = nullptr;  // fp32 only: TF32 hi / lo split of X for the 3xTF32 tensor path
-    // fp64 only, created on first use by the int8-slice tensor path (impl 6): digit planes [I8_S][N][ld8] and row scales
+    // created on first use by the int8-slice tensor path (impl 6): digit planes [S][N][ld8] (S = 7 for fp64, 4 for fp32) and row scales
     void *X_i8 = nullptr, *rscale = nullptr;
     std::size_t ld8 = 0;
     int i8_bad_rows = 0;  // rows whose elements are spread over too many orders of magnitude for the automatic choice (split_i8_kernel)
@@ -262,12 +262,12 @@ void make_tensor_map(plssvm_b200_ctx *ctx, CUtensorMap *tm, const T *base, const
     if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(rc))); }
 }
 
-// 3-D map over the int8 digit planes [I8_S][rows][ld8]: box = 64 bytes x `box_rows` rows x all planes, 64-byte swizzle
+// 3-D map over the int8 digit planes [planes][rows][ld8]: box = 64 bytes x `box_rows` rows x all planes, 64-byte swizzle
 void make_tensor_map_i8(plssvm_b200_ctx *ctx, CUtensorMap *tm, const std::int8_t *base, const std::size_t rows, const std::size_t ld8, const std::size_t plane_bytes,
-                        const std::uint32_t box_rows) {
-    const cuuint64_t dims[3] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(pb::I8_S) };
+                        const std::uint32_t box_rows, const std::uint32_t planes) {
+    const cuuint64_t dims[3] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes) };
     const cuuint64_t strides[2] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(plane_bytes) };
-    const cuuint32_t box[3] = { static_cast<cuuint32_t>(pb::I8_BK), box_rows, static_cast<cuuint32_t>(pb::I8_S) };
+    const cuuint32_t box[3] = { static_cast<cuuint32_t>(pb::I8_BK), box_rows, planes };
     const cuuint32_t estr[3] = { 1, 1, 1 };
     const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<std::int8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -276,28 +276,42 @@ void make_tensor_map_i8(plssvm_b200_ctx *ctx, CUtensorMap *tm, const std::int8_t
 
 inline std::size_t pitch_i8(const std::size_t d) { return (d + 127) / 128 * 128; }
 
-// fp64 rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold I8_S * rows * ld8 bytes
-void run_split_i8(plssvm_b200_ctx *ctx, const double *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8,
-                  double *rscale, int *bad_rows, cudaStream_t st) {
-    pb::split_i8_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(X, rows, static_cast<std::uint32_t>(d), static_cast<std::uint32_t>(ld), planes, rows * ld8,
-                                                                              static_cast<std::uint32_t>(ld8), rscale, bad_rows);
+// rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold I8<T>::S * rows * ld8 bytes
+template <typename T>
+void run_split_i8(plssvm_b200_ctx *ctx, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8, T *rscale,
+                  int *bad_rows, cudaStream_t st) {
+    pb::split_i8_kernel<T><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(X, rows, static_cast<std::uint32_t>(d), static_cast<std::uint32_t>(ld), planes, rows * ld8,
+                                                                                 static_cast<std::uint32_t>(ld8), rscale, bad_rows);
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
 }
 
-// digit planes of a resident fp64 data set, created on first use
+// digit planes of a resident data set, created on first use
+template <typename T>
 void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
     if (ds->X_i8 != nullptr) { return; }
     ds->ld8 = pitch_i8(ds->d);
-    PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(pb::I8_S) * ds->N * ds->ld8));
-    PB_CUDA(cudaMalloc(&ds->rscale, (ds->N + 1) * sizeof(double)));
-    int *range_d = reinterpret_cast<int *>(static_cast<double *>(ds->rscale) + ds->N);  // scratch word behind the scales
-    PB_CUDA(cudaMemsetAsync(range_d, 0, sizeof(int), ctx->stream));
-    run_split_i8(ctx, static_cast<const double *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<double *>(ds->rscale), range_d, ctx->stream);
+    PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(pb::I8<T>::S) * ds->N * ds->ld8));
+    PB_CUDA(cudaMalloc(&ds->rscale, (ds->N + 2) * sizeof(T)));
+    int *bad_d = reinterpret_cast<int *>(static_cast<T *>(ds->rscale) + ds->N);  // scratch word behind the scales
+    PB_CUDA(cudaMemsetAsync(bad_d, 0, sizeof(int), ctx->stream));
+    run_split_i8<T>(ctx, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<T *>(ds->rscale), bad_d, ctx->stream);
     int *h = static_cast<int *>(ctx->pinned) + 512;  // second half of the pinned block (the first holds the CG state read-back)
-    PB_CUDA(cudaMemcpyAsync(h, range_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PB_CUDA(cudaMemcpyAsync(h, bad_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
     ds->i8_bad_rows = *h;
+}
+
+// TF32 hi / lo split of a resident fp32 data set for the tcgen05 3xTF32 tiles (tile_tf32*.cuh), created on first use
+void ensure_tf32_split(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
+    if (ds->X_hi != nullptr || ds->elem_size != 4) { return; }
+    const std::size_t total = ds->N * ds->ld;
+    PB_CUDA(cudaMalloc(&ds->X_hi, total * sizeof(float)));
+    PB_CUDA(cudaMalloc(&ds->X_lo, total * sizeof(float)));
+    const unsigned grid = static_cast<unsigned>(std::min<std::size_t>((total + 255) / 256, static_cast<std::size_t>(ctx->num_sms) * 32));
+    pb::split_tf32_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float *>(ds->X), static_cast<float *>(ds->X_hi), static_cast<float *>(ds->X_lo), total);
+    PB_CUDA(cudaGetLastError());
+    ctx->tm.kernel_launches++;
 }
 
 // automatic kernel choice only: the int8-slice tiles are used unless the data set holds badly scaled rows (split_i8_kernel)
@@ -308,18 +322,19 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
     const std::uint64_t ntiles = p.tile_hi - p.tile_lo;
     if (ntiles == 0) { return; }
     const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
+    if (impl == 6) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 4, units of 128 x 128)
+        using L8 = pb::I8Layout<T>;
+        PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
+        CUtensorMap tmA, tmB;
+        make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE), static_cast<std::uint32_t>(L8::S));
+        make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(L8::NH), static_cast<std::uint32_t>(L8::S));
+        PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_i8<T, KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
+        pb::tile_kernel_i8<T, KERNEL, MODE><<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+        return;
+    }
     if constexpr (sizeof(T) == 8) {
-        if (impl == 6) {  // int8-slice tcgen05 tiles: units of 128 x 64, S exact int32 accumulators in TMEM
-            PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
-            CUtensorMap tmA, tmB;
-            make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE));
-            make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(pb::I8_NH));
-            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_i8<KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, pb::I8_SMEM_BYTES));
-            pb::tile_kernel_i8<KERNEL, MODE><<<grid, pb::I8_THREADS, pb::I8_SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
-            PB_CUDA(cudaGetLastError());
-            ctx->tm.kernel_launches++;
-            return;
-        }
         if (impl == 2) {
             CUtensorMap tmA, tmB;
             make_tensor_map<double>(ctx, &tmA, p.A, p.n_rows, p.ld);
@@ -370,13 +385,13 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
-    // int8-slice tcgen05 tiles exist for fp64 only; beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA tiles
-    if (ctx->impl == 6) { return (sizeof(T) == 8 && features <= pb::I8_MAX_FEATURES) ? 6 : 2; }
+    // int8-slice tcgen05 tiles: beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA / 3xTF32 tiles
+    if (ctx->impl == 6) { return features <= pb::I8_MAX_FEATURES ? 6 : 2; }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
-    // auto: fp64 -> int8 slices on tcgen05 (tile_i8.cuh) where the accumulators cannot overflow (callers fall back to 2 = TMA + DMMA,
-    // tile_dmma.cuh, for badly scaled rows: i8_allowed); fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
-    if (sizeof(T) == 8 && features > 0 && features <= pb::I8_MAX_FEATURES) { return 6; }
+    // auto: int8 slices on tcgen05 (tile_i8.cuh) where the int32 accumulators cannot overflow; callers fall back to 2 for badly scaled
+    // rows (i8_allowed): fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
+    if (features > 0 && features <= pb::I8_MAX_FEATURES) { return 6; }
     return 2;
 }
 
@@ -421,12 +436,11 @@ struct matvec_plan {
         Tb = (n + TILE - 1) / TILE;
         const bool tiles_needed = !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR);
         impl = resolve_impl<T>(c, data->ld);
-        if constexpr (sizeof(T) == 8) {
-            if (impl == 6 && tiles_needed) {
-                ensure_i8(c, const_cast<plssvm_b200_dataset *>(data));
-                if (!i8_allowed(c, data)) { impl = 2; }
-            }
+        if (impl == 6 && tiles_needed) {
+            ensure_i8<T>(c, const_cast<plssvm_b200_dataset *>(data));
+            if (!i8_allowed(c, data)) { impl = 2; }
         }
+        if (sizeof(T) == 4 && tiles_needed && (impl == 2 || impl == 4 || impl == 5)) { ensure_tf32_split(c, const_cast<plssvm_b200_dataset *>(data)); }
         tile_shift = (impl == 4 || impl == 5) ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
         pb::rank_range(pb::tri_num_tiles((Tb + tile_shift) >> tile_shift), c->rank, c->world, tile_lo, tile_hi);
         if (tiles_needed) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
@@ -435,13 +449,11 @@ struct matvec_plan {
         base.B = base.A;
         base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
         base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
-        if constexpr (sizeof(T) == 8) {
-            if (impl == 6 && tiles_needed) {
-                base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
-                base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
-                base.A_plane = base.B_plane = data->N * data->ld8;
-                base.ld8 = static_cast<std::uint32_t>(data->ld8);
-            }
+        if (impl == 6 && tiles_needed) {
+            base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
+            base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
+            base.A_plane = base.B_plane = data->N * data->ld8;
+            base.ld8 = static_cast<std::uint32_t>(data->ld8);
         }
         base.n_rows = n;
         base.n_cols = n;
@@ -570,16 +582,6 @@ plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const T *X, const std:
         pb::row_norms_kernel<T><<<static_cast<unsigned>((N + 7) / 8), 256, 0, ctx->stream>>>(static_cast<const T *>(ds->X), N, static_cast<std::uint32_t>(ds->ld), static_cast<T *>(ds->sq));
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches++;
-        if constexpr (sizeof(T) == 4) {
-            // TF32 hi / lo split for the tcgen05 3xTF32 tiles (done once per data set; X is constant across CG iterations)
-            PB_CUDA(cudaMalloc(&ds->X_hi, N * ds->ld * sizeof(T)));
-            PB_CUDA(cudaMalloc(&ds->X_lo, N * ds->ld * sizeof(T)));
-            const std::size_t total = N * ds->ld;
-            const unsigned grid = static_cast<unsigned>(std::min<std::size_t>((total + 255) / 256, static_cast<std::size_t>(ctx->num_sms) * 32));
-            pb::split_tf32_kernel<<<grid, 256, 0, ctx->stream>>>(static_cast<const float *>(ds->X), static_cast<float *>(ds->X_hi), static_cast<float *>(ds->X_lo), total);
-            PB_CUDA(cudaGetLastError());
-            ctx->tm.kernel_launches++;
-        }
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
         cudaFree(ds->X);
@@ -801,17 +803,15 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
     if (impl == 4 || impl == 5) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
-    if constexpr (sizeof(T) == 8) {
-        if (impl == 6) {
-            PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
-            p.A_i8 = P_i8;
-            p.A_scale = P_scale;
-            p.A_plane = P_plane;
-            p.B_i8 = static_cast<const std::int8_t *>(sv->X_i8);
-            p.B_scale = static_cast<const T *>(sv->rscale);
-            p.B_plane = sv->N * sv->ld8;
-            p.ld8 = static_cast<std::uint32_t>(sv->ld8);
-        }
+    if (impl == 6) {
+        PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
+        p.A_i8 = P_i8;
+        p.A_scale = P_scale;
+        p.A_plane = P_plane;
+        p.B_i8 = static_cast<const std::int8_t *>(sv->X_i8);
+        p.B_scale = static_cast<const T *>(sv->rscale);
+        p.B_plane = sv->N * sv->ld8;
+        p.ld8 = static_cast<std::uint32_t>(sv->ld8);
     }
     p.row_sq = P_sq;
     p.col_sq = static_cast<const T *>(sv->sq);
@@ -872,16 +872,18 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     constexpr std::size_t SUPER_BATCH = std::size_t{ 1 } << 22;
     const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
-    const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && resolve_impl<T>(ctx) >= 2;  // every tcgen05 variant (impl 2, 4, 5) consumes the hi / lo split
     int impl = resolve_impl<T>(ctx, sv->ld);
-    if constexpr (sizeof(T) == 8) {
-        if (impl == 6 && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
-            ensure_i8(ctx, sv);
-            if (pts_ds != nullptr) { ensure_i8(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
-            if (!i8_allowed(ctx, sv) || (pts_ds != nullptr && !i8_allowed(ctx, pts_ds))) { impl = 2; }
-        }
+    if (impl == 6 && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
+        ensure_i8<T>(ctx, sv);
+        if (pts_ds != nullptr) { ensure_i8<T>(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
+        if (!i8_allowed(ctx, sv) || (pts_ds != nullptr && !i8_allowed(ctx, pts_ds))) { impl = 2; }
     }
-    const bool need_i8 = sizeof(T) == 8 && kernel != pb::K_LINEAR && impl == 6;
+    const bool need_i8 = kernel != pb::K_LINEAR && impl == 6;
+    const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && (impl == 2 || impl == 4 || impl == 5);  // the 3xTF32 tcgen05 variants consume the hi / lo split
+    if (need_split) {
+        ensure_tf32_split(ctx, sv);
+        if (pts_ds != nullptr) { ensure_tf32_split(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
+    }
     const std::size_t ld8 = pitch_i8(sv->d);
     std::int8_t *stage_i8[2] = { nullptr, nullptr };
     T *stage_sc[2] = { nullptr, nullptr };
@@ -895,7 +897,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                 stage_lo[i] = workspace<T>(ctx, ctx_t::WS_LO0 + i, stage_rows * sv->ld);
             }
             if (need_i8) {
-                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8_S) * stage_rows * ld8);
+                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8<T>::S) * stage_rows * ld8);
                 stage_sc[i] = workspace<T>(ctx, ctx_t::WS_SC0 + i, stage_rows);
             }
             if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X[i], 0, stage_rows * sv->ld * sizeof(T), st)); }  // pad columns stay zero
@@ -948,13 +950,11 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                         ctx->tm.kernel_launches++;
                     }
                 }
-                if constexpr (sizeof(T) == 8) {
-                    if (need_i8) {
-                        run_split_i8(ctx, stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], nullptr, st);
-                        P_i8 = stage_i8[buf];
-                        P_scale = stage_sc[buf];
-                        P_plane = mb * ld8;
-                    }
+                if (need_i8) {
+                    run_split_i8<T>(ctx, stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], nullptr, st);
+                    P_i8 = stage_i8[buf];
+                    P_scale = stage_sc[buf];
+                    P_plane = mb * ld8;
                 }
                 P = stage_X[buf];
                 P_sq = stage_sq[buf];

@@ -1,5 +1,6 @@
-// fp64-accurate tile kernel of the implicit kernel matrix on the 5th-generation tensor cores: tcgen05.mma kind::i8 over
+// Tile kernel of the implicit kernel matrix on the 5th-generation tensor cores for BOTH real types: tcgen05.mma kind::i8 over
 // int8 slices of X (an Ozaki-style error-free splitting), exact int32 accumulation in TMEM, fp64 recombination in the epilogue.
+// fp64: S = 7 slices (54 fractional bits), 128 x 64 units; fp32: S = 4 slices (30 bits — more than the 24 of the inputs), 128 x 128 units.
 //
 // Why: tcgen05.mma has no f64 kind and the FP64 pipes of B200 (DMMA == DFMA) stop at ~37 TFLOP/s; the int8 tensor pipe is
 // ~120x faster.  Every row x_i is written once per data set (split_i8_kernel) as a fixed-point number relative to its own
@@ -33,43 +34,62 @@
 
 namespace pb {
 
-constexpr int I8_S = 7;                                    // int8 slices per operand (8 S - 2 = 54 fractional bits)
 constexpr int I8_BK = 64;                                  // bytes (= features) per slab: one SWIZZLE_64B row, two K = 32 MMA steps
-constexpr int I8_NH = 64;                                  // columns per unit (half a tile)
-constexpr int I8_STAGES = 2;
-constexpr int I8_A_SLICE = TILE * I8_BK;                   // 8 KiB
-constexpr int I8_B_SLICE = I8_NH * I8_BK;                  // 4 KiB
-constexpr int I8_A_BYTES = I8_S * I8_A_SLICE;              // 56 KiB
-constexpr int I8_B_BYTES = I8_S * I8_B_SLICE;              // 28 KiB
-constexpr int I8_STAGE_BYTES = I8_A_BYTES + I8_B_BYTES;    // 84 KiB
 constexpr int I8_THREADS = 320;                            // producer warp, MMA warp, 8 epilogue warps
 constexpr int I8_EPI_THREADS = 256;
-constexpr int I8_VEC_BYTES = (4 * TILE + 4 * I8_NH + 4 * I8_NH + TILE) * 8;  // row vectors, column vectors, column sums, row sums
-constexpr int I8_SMEM_BYTES = 1024 + I8_STAGES * I8_STAGE_BYTES + I8_VEC_BYTES + (2 * I8_STAGES + 2) * 8 + 16;
 constexpr std::uint32_t I8_TMEM_COLS = 512;
-constexpr std::uint32_t I8_MAX_FEATURES = 16384;           // 7 products of <= 2^14 per feature and diagonal stay below 2^31
+constexpr std::uint32_t I8_MAX_FEATURES = 16384;           // <= 7 products of <= 2^14 per feature and diagonal stay below 2^31
 constexpr int I8_AUTO_MAX_RANGE = 20;                      // automatic choice: see split_i8_kernel (badly scaled rows -> DMMA tiles)
 
-static_assert(I8_S * I8_NH <= 512, "accumulators must fit into TMEM");
-static_assert(I8_STAGE_BYTES % 1024 == 0, "stage alignment");
+// per real type: number of slices S (8 S - 2 fractional bits relative to the row maximum) and unit width NH (S * NH <= 512 TMEM columns)
+template <typename T>
+struct I8;
+template <>
+struct I8<double> {
+    static constexpr int S = 7, NH = 64;
+};
+template <>
+struct I8<float> {
+    static constexpr int S = 4, NH = 128;
+};
+template <typename T>
+struct I8Layout {
+    static constexpr int S = I8<T>::S, NH = I8<T>::NH;
+    static constexpr int UNITS = TILE / NH;                     // units per 128 x 128 tile of the schedule
+    static constexpr int A_SLICE = TILE * I8_BK;                // 8 KiB
+    static constexpr int B_SLICE = NH * I8_BK;
+    static constexpr int A_BYTES = S * A_SLICE;
+    static constexpr int B_BYTES = S * B_SLICE;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // fp64: 84 KiB, fp32: 64 KiB
+    static constexpr int VEC_BYTES = (4 * TILE + 4 * NH + 4 * NH + TILE) * static_cast<int>(sizeof(T));  // row vectors, column vectors, column sums, row sums
+    static constexpr int STAGES = (227 * 1024 - 1024 - VEC_BYTES - 256) / STAGE_BYTES;                   // fp64: 2, fp32: 3
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + VEC_BYTES + (2 * STAGES + 2) * 8 + 16;
+    static constexpr int SLICES_PER_MMA = 256 / NH;             // B slices one N <= 256 instruction covers
+    static constexpr int CPT = NH / 2;                          // columns per epilogue thread
+    static_assert(S * NH <= 512, "accumulators must fit into TMEM");
+    static_assert(STAGE_BYTES % 1024 == 0 && STAGES >= 2, "stage layout");
+    static_assert(VEC_BYTES % 8 == 0 && CPT % 32 == 0, "epilogue layout");
+};
 
-// ---- operand preparation: fp64 rows -> S int8 digit planes + per-row scale ------------------------------------------------
+// ---- operand preparation: rows -> S int8 digit planes + per-row scale ---------------------------------------------------------
 // planes[p][row][k] (row pitch ld8 bytes, zero padded), rscale[row] = 2^(e_row - 6); one warp per row.
-// The products are accurate to ~2^-54 sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
+// The products are accurate to ~2^-(8S-2) sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
 // which is at most the row norm), but elements far below their row's maximum keep fewer significant bits of their own.
 // bad_rows (optional) counts the rows where more than 1 / 16 of the non-zero elements lie more than 2^I8_AUTO_MAX_RANGE below the
-// largest one; the automatic kernel choice falls back to the DMMA tiles for such badly scaled data.
-// Rows containing inf / NaN get a NaN scale, so they poison their results exactly like native fp64 arithmetic would.
-__global__ void __launch_bounds__(256) split_i8_kernel(const double *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
+// largest one; the automatic kernel choice falls back to the DMMA tiles for such badly scaled fp64 data.
+// Rows containing inf / NaN get a NaN scale, so they poison their results exactly like native floating-point arithmetic would.
+template <typename T>
+__global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
                                                        std::int8_t *__restrict__ planes, const std::size_t plane_stride, const std::uint32_t ld8,
-                                                       double *__restrict__ rscale, int *__restrict__ bad_rows) {
+                                                       T *__restrict__ rscale, int *__restrict__ bad_rows) {
+    constexpr int S = I8<T>::S;
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) { return; }
     const int lane = threadIdx.x & 31;
-    const double *x = X + row * ld;
+    const T *x = X + row * ld;
     double mx = 0.0, poison = 0.0;
     for (std::uint32_t k = lane; k < d; k += 32) {
-        const double ax = fabs(x[k]);
+        const double ax = fabs(static_cast<double>(x[k]));
         mx = fmax(mx, ax);
         poison += ax * 0.0;  // NaN iff the row holds an inf or a NaN
     }
@@ -83,26 +103,27 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const double *__restrict_
     int e = 0;
     if (mx > 0.0) { (void) frexp(mx, &e); }  // mx = m 2^e, m in [0.5, 1)  =>  |x_k| < 2^e
     e = e < -900 ? -900 : e;
-    const double to_fixed = bad ? 0.0 : ldexp(1.0, (8 * I8_S - 2) - e);
+    if (sizeof(T) == 4) { e = e < -100 ? -100 : e; }  // keep the scale a normal float
+    const double to_fixed = bad ? 0.0 : ldexp(1.0, (8 * S - 2) - e);
     const double small = ldexp(1.0, e - I8_AUTO_MAX_RANGE);
-    if (lane == 0) { rscale[row] = bad ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, e - 6); }
+    if (lane == 0) { rscale[row] = bad ? static_cast<T>(__longlong_as_double(0x7ff8000000000000ll)) : static_cast<T>(ldexp(1.0, e - 6)); }
     std::int8_t *out = planes + row * ld8;
     unsigned n_nonzero = 0, n_small = 0;
     for (std::uint32_t k0 = 4u * lane; k0 < ld8; k0 += 128u) {
         long long v[4];
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double xv = (k0 + j < d && !bad) ? x[k0 + j] : 0.0;
+            const double xv = (k0 + j < d && !bad) ? static_cast<double>(x[k0 + j]) : 0.0;
             n_nonzero += xv != 0.0 ? 1u : 0u;
             n_small += (xv != 0.0 && fabs(xv) < small) ? 1u : 0u;
             v[j] = __double2ll_rn(xv * to_fixed);
         }
         #pragma unroll
-        for (int p = 0; p < I8_S; ++p) {
+        for (int p = 0; p < S; ++p) {
             std::uint32_t word = 0;
             #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const long long a = (p == I8_S - 1) ? v[j] : static_cast<long long>(static_cast<signed char>(v[j] & 0xFF));  // balanced digit in [-128, 127]
+                const long long a = (p == S - 1) ? v[j] : static_cast<long long>(static_cast<signed char>(v[j] & 0xFF));  // balanced digit in [-128, 127]
                 word |= (static_cast<std::uint32_t>(a) & 0xFFu) << (8 * j);
                 v[j] = (v[j] - a) >> 8;  // exact
             }
@@ -152,29 +173,31 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // exact int32 -> fp64 on the FP64 add pipe: (2^52 + 2^31 + a) - (2^52 + 2^31)
 __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __hiloint2double(0x43300000, static_cast<int>(a ^ 0x80000000u)) - 4503601774854144.0; }
 
-template <int KERNEL, int MODE>
+template <typename T, int KERNEL, int MODE>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<double> p) {
+tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<T> p) {
+    using L8 = I8Layout<T>;
+    constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT;
     extern __shared__ unsigned char smem_raw[];
     if (p.done != nullptr && *p.done != 0) { return; }
 
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char *stages = smem;
-    double *s_row = reinterpret_cast<double *>(smem + I8_STAGES * I8_STAGE_BYTES);  // [4][TILE]: q_i, v_i, sq_i, scale_i
-    double *s_col = s_row + 4 * TILE;                                                // [4][I8_NH]: q_j, v_j, sq_j, scale_j
-    double *s_colsum = s_col + 4 * I8_NH;                                            // [4][I8_NH]
-    double *s_rowsum = s_colsum + 4 * I8_NH;                                         // [TILE]
-    std::uint64_t *bars = reinterpret_cast<std::uint64_t *>(s_rowsum + TILE);        // full[S], empty[S], tmem_full, tmem_empty
-    std::uint32_t *tmem_slot = reinterpret_cast<std::uint32_t *>(bars + 2 * I8_STAGES + 2);
-    const std::uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + I8_STAGES);
-    const std::uint32_t tfull = smem_u32(bars + 2 * I8_STAGES), tempty = smem_u32(bars + 2 * I8_STAGES + 1);
+    T *s_row = reinterpret_cast<T *>(smem + STAGES * L8::STAGE_BYTES);            // [4][TILE]: q_i, v_i, sq_i, scale_i
+    T *s_col = s_row + 4 * TILE;                                                   // [4][NH]: q_j, v_j, sq_j, scale_j
+    T *s_colsum = s_col + 4 * NH;                                                  // [4][NH]
+    T *s_rowsum = s_colsum + 4 * NH;                                               // [TILE]
+    std::uint64_t *bars = reinterpret_cast<std::uint64_t *>(s_rowsum + TILE);      // full[STAGES], empty[STAGES], tmem_full, tmem_empty
+    std::uint32_t *tmem_slot = reinterpret_cast<std::uint32_t *>(bars + 2 * STAGES + 2);
+    const std::uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const std::uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const std::uint32_t num_slabs = (p.ld8 + I8_BK - 1) / I8_BK;
 
     if (tid == 0) {
         #pragma unroll
-        for (int s = 0; s < I8_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
@@ -203,16 +226,16 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else {
                     rect_decode(p.T_rows, p.T_cols, L, I, J);
                 }
-                for (int h = 0; h < 2; ++h) {
-                    const int ra = static_cast<int>(I * TILE), rb = static_cast<int>(J * TILE + h * I8_NH);
+                for (int h = 0; h < UNITS; ++h) {
+                    const int ra = static_cast<int>(I * TILE), rb = static_cast<int>(J * TILE + h * NH);
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1u);
-                        const std::uint32_t dst = smem_u32(stages + stage * I8_STAGE_BYTES);
+                        const std::uint32_t dst = smem_u32(stages + stage * L8::STAGE_BYTES);
                         const std::uint32_t bar = full0 + 8 * stage;
-                        mbar_arrive_expect_tx(bar, I8_STAGE_BYTES);
+                        mbar_arrive_expect_tx(bar, L8::STAGE_BYTES);
                         tma_load_3d(dst, &tmA, static_cast<int>(ks * I8_BK), ra, 0, bar);
-                        tma_load_3d(dst + I8_A_BYTES, &tmB, static_cast<int>(ks * I8_BK), rb, 0, bar);
-                        if (++stage == I8_STAGES) {
+                        tma_load_3d(dst + L8::A_BYTES, &tmB, static_cast<int>(ks * I8_BK), rb, 0, bar);
+                        if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -226,33 +249,33 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             std::uint32_t stage = 0, phase = 0, unit_iter = 0;
             for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
-                for (int h = 0; h < 2; ++h, ++unit_iter) {
+                for (int h = 0; h < UNITS; ++h, ++unit_iter) {
                     mbar_wait(tempty, (unit_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous unit
                     tcgen05_fence_after();
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
                         mbar_wait(full0 + 8 * stage, phase);
                         tcgen05_fence_after();
-                        const std::uint32_t base = smem_u32(stages + stage * I8_STAGE_BYTES);
-                        const std::uint64_t d_a = umma_desc_sw64(base), d_b = umma_desc_sw64(base + I8_A_BYTES);
+                        const std::uint32_t base = smem_u32(stages + stage * L8::STAGE_BYTES);
+                        const std::uint64_t d_a = umma_desc_sw64(base), d_b = umma_desc_sw64(base + L8::A_BYTES);
                         #pragma unroll
                         for (std::uint32_t k = 0; k < I8_BK / 32; ++k) {
                             const std::uint64_t koff = static_cast<std::uint64_t>((k * 32) >> 4);  // 32 bytes per K = 32 step inside the swizzle atom
                             const bool first = (ks | k) == 0u;
                             // slice A_p times the slices B_q, q = S-1-p .. S-1, lands in the accumulators t' = 0 .. p (N <= 256 per instruction)
                             #pragma unroll
-                            for (int pp = I8_S - 1; pp >= 0; --pp) {
-                                const int q_lo = I8_S - 1 - pp, cnt = pp + 1;
+                            for (int pp = S - 1; pp >= 0; --pp) {
+                                const int q_lo = S - 1 - pp, cnt = pp + 1;
                                 #pragma unroll
-                                for (int c = 0; 4 * c < cnt; ++c) {
-                                    const int nsl = cnt - 4 * c < 4 ? cnt - 4 * c : 4;
-                                    umma_i8(tmem_base + static_cast<std::uint32_t>(c * 4 * I8_NH), d_a + koff + static_cast<std::uint64_t>((pp * I8_A_SLICE) >> 4),
-                                            d_b + koff + static_cast<std::uint64_t>(((q_lo + 4 * c) * I8_B_SLICE) >> 4), i8_idesc(static_cast<std::uint32_t>(nsl * I8_NH)),
-                                            (first && pp == I8_S - 1) ? 0u : 1u);
+                                for (int c = 0; L8::SLICES_PER_MMA * c < cnt; ++c) {
+                                    const int nsl = cnt - L8::SLICES_PER_MMA * c < L8::SLICES_PER_MMA ? cnt - L8::SLICES_PER_MMA * c : L8::SLICES_PER_MMA;
+                                    umma_i8(tmem_base + static_cast<std::uint32_t>(c * L8::SLICES_PER_MMA * NH), d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4),
+                                            d_b + koff + static_cast<std::uint64_t>(((q_lo + L8::SLICES_PER_MMA * c) * L8::B_SLICE) >> 4), i8_idesc(static_cast<std::uint32_t>(nsl * NH)),
+                                            (first && pp == S - 1) ? 0u : 1u);
                                 }
                             }
                         }
                         umma_commit(empty0 + 8 * stage);  // smem stage reusable once these MMAs have read it
-                        if (++stage == I8_STAGES) {
+                        if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
                         }
@@ -263,7 +286,7 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns 32 ch .. + 31 of the unit =====
+        // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns CPT ch .. + CPT - 1 of the unit =====
         const int quarter = warp & 3;
         const int ch = (warp - 2) >> 2;        // column half of the unit
         const int row = quarter * 32 + lane;   // accumulator row of this thread
@@ -278,48 +301,49 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const std::uint32_t row0 = I * TILE;
             const bool diag = (MODE == MODE_SYM) && (I == J);
-            const double qa = (MODE == MODE_SYM) ? *p.QA_cost : 0.0;
-            double rowacc = 0.0;
-            for (int h = 0; h < 2; ++h, ++unit_iter) {
-                const std::uint32_t col0 = J * TILE + h * I8_NH;
+            const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
+            T rowacc = T(0);
+            for (int h = 0; h < UNITS; ++h, ++unit_iter) {
+                const std::uint32_t col0 = J * TILE + h * NH;
                 if (h == 0 && et < TILE) {
                     const std::uint32_t gi = row0 + et;
                     const bool oki = gi < p.n_rows;
-                    s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : 0.0;
-                    s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : 0.0;
-                    s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : 0.0;
-                    s_row[3 * TILE + et] = oki ? p.A_scale[gi] : 0.0;
+                    s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : T(0);
+                    s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : T(0);
+                    s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : T(0);
+                    s_row[3 * TILE + et] = oki ? p.A_scale[gi] : T(0);
                 }
-                if (et >= TILE && et < TILE + I8_NH) {
+                if (et >= TILE && et < TILE + NH) {
                     const int c = et - TILE;
                     const std::uint32_t gj = col0 + c;
                     const bool okj = gj < p.n_cols;
-                    s_col[0 * I8_NH + c] = (MODE == MODE_SYM && okj) ? p.q[gj] : 0.0;
-                    s_col[1 * I8_NH + c] = okj ? p.v[gj] : 0.0;
-                    s_col[2 * I8_NH + c] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : 0.0;
-                    s_col[3 * I8_NH + c] = okj ? p.B_scale[gj] : 0.0;
+                    s_col[0 * NH + c] = (MODE == MODE_SYM && okj) ? p.q[gj] : T(0);
+                    s_col[1 * NH + c] = okj ? p.v[gj] : T(0);
+                    s_col[2 * NH + c] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : T(0);
+                    s_col[3 * NH + c] = okj ? p.B_scale[gj] : T(0);
                 }
                 named_bar_sync(1, I8_EPI_THREADS);
-                const double qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row], sci = s_row[3 * TILE + row];
+                const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row], sci = s_row[3 * TILE + row];
 
                 mbar_wait(tfull, unit_iter & 1u);
                 tcgen05_fence_after();
-                const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * 32);
+                const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * CPT);
 
-                // phase 1: S int32 diagonals -> one fp64 value per element (Horner from the least significant diagonal)
-                double a[32];
+                // phase 1: S int32 diagonals -> one value per element (Horner in fp64 from the least significant diagonal: every step exact
+                // up to one rounding relative to the running sum)
+                T a[CPT];
                 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    std::uint32_t r[I8_S][8];
+                for (int g = 0; g < CPT / 8; ++g) {
+                    std::uint32_t r[S][8];
                     #pragma unroll
-                    for (int t = 0; t < I8_S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * I8_NH + g * 8), r[t]); }
+                    for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
                     tmem_ld_wait();
                     #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         double s = i32_to_f64(r[0][j]);
                         #pragma unroll
-                        for (int t = 1; t < I8_S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
-                        a[g * 8 + j] = s;
+                        for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
+                        a[g * 8 + j] = static_cast<T>(s);
                     }
                 }
                 // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp
@@ -329,46 +353,49 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
                 // phase 2: kernel function and the weighted sums
                 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int cl = ch * 32 + j;
-                    const double dot = a[j] * (sci * s_col[3 * I8_NH + cl]);
-                    const double kv = kernel_from_dot<KERNEL>(dot, sqi, s_col[2 * I8_NH + cl], p.kp);
-                    double t = kv;
+                for (int j = 0; j < CPT; ++j) {
+                    const int cl = ch * CPT + j;
+                    const T dot = a[j] * (sci * s_col[3 * NH + cl]);
+                    const T kv = kernel_from_dot<KERNEL>(dot, sqi, s_col[2 * NH + cl], p.kp);
+                    T t = kv;
                     if constexpr (MODE == MODE_SYM) {
-                        t = kv + qa - qi - s_col[0 * I8_NH + cl];
-                        if (diag && row == h * I8_NH + cl) { t += p.cost_inv; }
+                        t = kv + qa - qi - s_col[0 * NH + cl];
+                        if (diag && row == h * NH + cl) { t += p.cost_inv; }
                     }
-                    rowacc = fma(t, s_col[1 * I8_NH + cl], rowacc);
+                    rowacc = pb_fma(t, s_col[1 * NH + cl], rowacc);
                     a[j] = t * vi;  // mirrored contribution of this row to column cl
                 }
                 if constexpr (MODE == MODE_SYM) {
                     if (!diag) {  // CTA-uniform
-                        // butterfly: after 5 halving steps lane c holds the sum over the warp's 32 rows of column ch * 32 + c
+                        // butterfly per 32 columns: after 5 halving steps lane c holds the sum over the warp's 32 rows of column c
                         #pragma unroll
-                        for (int step = 16; step >= 1; step >>= 1) {
-                            const bool upper = (lane & step) != 0;
+                        for (int cc = 0; cc < CPT / 32; ++cc) {
                             #pragma unroll
-                            for (int k = 0; k < step; ++k) {
-                                const double send = upper ? a[k] : a[k + step];
-                                const double keep = upper ? a[k + step] : a[k];
-                                a[k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                            for (int step = 16; step >= 1; step >>= 1) {
+                                const bool upper = (lane & step) != 0;
+                                #pragma unroll
+                                for (int k = 0; k < step; ++k) {
+                                    const T send = upper ? a[cc * 32 + k] : a[cc * 32 + k + step];
+                                    const T keep = upper ? a[cc * 32 + k + step] : a[cc * 32 + k];
+                                    a[cc * 32 + k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                                }
                             }
+                            s_colsum[quarter * NH + ch * CPT + cc * 32 + lane] = a[cc * 32];
                         }
-                        s_colsum[quarter * I8_NH + ch * 32 + lane] = a[0];
                     }
                 }
-                if (h == 1 && ch == 1) { s_rowsum[row] = rowacc; }
+                if (h == UNITS - 1 && ch == 1) { s_rowsum[row] = rowacc; }
                 named_bar_sync(1, I8_EPI_THREADS);  // column sums of the four row quarters / row sums of the second column half visible
                 if constexpr (MODE == MODE_SYM) {
-                    if (!diag && et < I8_NH) {
-                        const double s = ((s_colsum[et] + s_colsum[I8_NH + et]) + s_colsum[2 * I8_NH + et]) + s_colsum[3 * I8_NH + et];
+                    if (!diag && et < NH) {
+                        const T s = ((s_colsum[et] + s_colsum[NH + et]) + s_colsum[2 * NH + et]) + s_colsum[3 * NH + et];
                         const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
-                        p.partial[mslot * TILE + h * I8_NH + et] = (col0 + et < p.n_cols) ? s : 0.0;
+                        p.partial[mslot * TILE + h * NH + et] = (col0 + et < p.n_cols) ? s : T(0);
                     }
                 }
-                if (h == 1 && ch == 0) {
+                if (h == UNITS - 1 && ch == 0) {
                     const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
-                    p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : 0.0;
+                    p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : T(0);
                 }
                 named_bar_sync(1, I8_EPI_THREADS);  // s_col / s_colsum / s_rowsum consumed before the next unit overwrites them
             }

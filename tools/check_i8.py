@@ -85,3 +85,54 @@ for (N, d, kernel) in ((16385, 4096, "rbf"),) if quick else ((16385, 4096, "rbf"
             print("   |i8 - dmma| / scale =", float(np.max(np.abs(out - ref)) / np.max(np.abs(ref))), flush=True)
     be.set_option("impl", 0)
     del ds
+
+# ---- fp32 through int8 slices (S = 4) vs the 3xTF32 tiles -------------------------------------------------------------------------
+worst32 = 0.0
+for (N, d) in ((2, 3), (130, 1), (386, 65), (1000, 96), (2049, 333)):
+    for kernel, kid in (("linear", 0), ("polynomial", 1), ("rbf", 2)):
+        X, y = make_data(N, d, 7, np.float32)
+        if N > 300:
+            X[3] *= 1e-3
+            X[5] *= 30.0
+        n = N - 1
+        ds = be.dataset(X)
+        q, k_last = be.run_q_kernel(ds, kernel)
+        v = np.random.default_rng(3).uniform(1, 2, n).astype(np.float32)
+        outs = {}
+        for impl in (1, 2, 6):
+            be.set_option("impl", impl)
+            outs[impl] = be.run_svm_kernel(ds, q, v, np.zeros_like(v), k_last + 1.0, 1.0, 1.0, kernel)
+        be.set_option("impl", 0)
+        want = orc.matvec(kid, X.astype(np.float64), q.astype(np.float64), v.astype(np.float64), np.zeros(n), float(k_last) + 1.0, 1.0, 1.0, gamma=1.0 / d)
+        sc = np.max(np.abs(want))
+        e = {i: np.max(np.abs(outs[i] - want)) / sc for i in outs}
+        worst32 = max(worst32, e[6])
+        print(f"fp32 N={N:5d} d={d:4d} {kernel:10s} simt {e[1]:.2e}  tf32x3 {e[2]:.2e}  i8 {e[6]:.2e}  (vs fp64 oracle)", flush=True)
+print("worst fp32 i8 matvec error:", worst32, "OK" if worst32 < 2e-6 else "FAIL", flush=True)
+X, y = make_data(3000, 200, 11, np.float32)
+P, _ = make_data(700, 200, 10, np.float32)
+alpha = np.random.default_rng(5).standard_normal(3000).astype(np.float32)
+for kernel in ("polynomial", "rbf"):
+    vals = {}
+    for impl in (2, 6):
+        be.set_option("impl", impl)
+        vals[impl], _ = be.predict_values(be.dataset(X), alpha, 0.1, be.dataset(P), kernel)
+        vals[(impl, "host")], _ = be.predict_values(X, alpha, 0.1, P, kernel)
+    sc = np.max(np.abs(vals[2]))
+    print(f"fp32 predict {kernel}: |i8 - tf32x3| / scale = {np.max(np.abs(vals[6] - vals[2])) / sc:.2e}   host-staged: {np.max(np.abs(vals[(6, 'host')] - vals[2])) / sc:.2e}", flush=True)
+be.set_option("impl", 0)
+for (N, d, kernel) in ((32769, 1024, "polynomial"), (32769, 4096, "rbf")):
+    X, y = make_data(N, d, 9, np.float32)
+    ds = be.dataset(X)
+    q, k_last = be.run_q_kernel(ds, kernel)
+    v = np.ones(N - 1, np.float32)
+    for impl in (2, 6):
+        be.set_option("impl", impl)
+        ts = []
+        for _ in range(4):
+            out = be.run_svm_kernel(ds, q, v, np.zeros_like(v), k_last + 1.0, 1.0, 1.0, kernel)
+            t = be.timings()
+            ts.append(t["matvec_tile_ms"])
+        print(f"fp32 {N}x{d} {kernel} impl {impl}: tile kernel {min(ts):.3f} ms -> {t['matvec_flops'] / min(ts) / 1e9:.1f} TFLOP/s  all: {[round(x, 3) for x in ts]}", flush=True)
+    be.set_option("impl", 0)
+    del ds
