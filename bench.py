@@ -312,7 +312,7 @@ def run_ours(args):
     peaks_path = os.path.join(ROOT, "profiles", "peaks_b200.json")
     peak, peak_src = 37.0, "vendor figure (fallback: profiles/peaks_b200.json missing)"
     impl_used = t_after["impl_used"]
-    tensor = impl_used in (2, 6)
+    tensor = impl_used in (2, 6, 7)
     key = "dmma_tflops_sustained_3s" if dtype == "float64" else ("cublas_sgemm_tf32_random_tflops_sustained_4s" if tensor else "ffma_tflops")
     pk = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
     if key in pk:
@@ -320,10 +320,10 @@ def run_ours(args):
         if dtype != "float64" and tensor:  # 3xTF32: three TF32 MMAs per algorithmic fp32 product
             peak, peak_src = peak / 3.0, peak_src + " / 3 (3xTF32 split)"
     fp_pipe_peak = peak  # fp64: DMMA issue peak; fp32: TF32 tensor peak / 3
-    i8_products = 28.0 if dtype == "float64" else 10.0
-    if impl_used == 6:
-        # int8-slice tiles: 28 (fp64: S = 7 slices, digit diagonals p + q >= 6) or 10 (fp32: S = 4) int8 tensor-core MACs per algorithmic MAC,
-        # so the roofline of this kernel is the int8 tensor pipe / 28 (/ 10): tcgen05.mma kind::i8 issue-loop peak with random operands, measured
+    i8_products = 28.0 if dtype == "float64" else (10.0 if impl_used == 7 else 6.0)
+    if impl_used in (6, 7):
+        # int8-slice tiles: 28 (fp64: S = 7 slices, digit diagonals p + q >= 6), 6 (fp32: S = 3) or 10 (fp32 with --tile-impl 7: S = 4) int8
+        # tensor-core MACs per algorithmic MAC, so the roofline of this kernel is the int8 tensor pipe / 28 (/ 6, / 10): tcgen05.mma kind::i8 issue-loop peak with random operands, measured
         # by tools/i8_peak_probe (burst when the kernel is timed alone, the sustained figure inside a long step; profiles/r01/i8_peaks_b200.json)
         i8_path = os.path.join(ROOT, "profiles", "r01", "i8_peaks_b200.json")
         i8 = json.load(open(i8_path)) if os.path.exists(i8_path) else {}
@@ -350,11 +350,12 @@ def run_ours(args):
         if world > 1:
             dist.destroy_process_group()
         return
-    kname = {6: f"tile_kernel_i8 ({'fp64' if dtype == 'float64' else 'fp32'} through int8 slices, tcgen05 kind::i8)", 2: "tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)"}.get(impl_used)
+    i8_name = f"tile_kernel_i8 ({'fp64' if dtype == 'float64' else 'fp32'} through {7 if dtype == 'float64' else (4 if impl_used == 7 else 3)} int8 slices, tcgen05 kind::i8)"
+    kname = {6: i8_name, 7: i8_name, 2: "tile_kernel_dmma" if dtype == "float64" else "tile_kernel_tf32 (tcgen05 3xTF32)"}.get(impl_used)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic if impl_used == 2 else None,
                 "kernel": kname + f"<{kernel}, sym>" if tensor else "tile_kernel_simt", "peak_source": peak_src,
                 "avg_launch_ms": avg_tile_s * 1e3, "launches_timed": int(tile_calls), "flops_per_launch": F / world}
-    if impl_used == 6:
+    if impl_used in (6, 7):
         roofline["int8_tops"] = achieved * i8_products
         # > 1: the result is produced faster than the floating-point pipe of that precision could (fp64: DMMA = DFMA issue peak; fp32: TF32 tensor peak / 3)
         roofline["vs_float_pipe_peak"] = achieved / fp_pipe_peak
@@ -419,8 +420,11 @@ def run_ours(args):
         "final_residual": float(res["delta"]), "tile_impl": int(t_after["impl_used"]), "full_solve": full,
         "precision_note": (("fp64 storage, vectors and epilogue; x_i.x_j through 7 int8 digit planes per operand, 28 exact int32 tensor-core products recombined in fp64 "
                             "(error vs the fp64 oracle <= that of the DMMA tiles)" if impl_used == 6 else None) if dtype == "float64" else
-                           ("fp32 storage, vectors and epilogue; x_i.x_j through 4 int8 digit planes per operand (30 bits), 10 exact int32 tensor-core products recombined in fp64, rounded "
-                            "once to fp32 (error vs the fp64 oracle ~2e-7, below the 3xTF32 tiles)" if impl_used == 6 else
+                           ("fp32 storage, vectors and epilogue; x_i.x_j through 3 int8 digit planes per operand (22 bits relative to the row maximum = the input precision of the 3xTF32 "
+                            "scheme), 6 exact int32 tensor-core products recombined in fp64, rounded once to fp32 (error vs the fp64 oracle ~2e-7: at or below the 3xTF32 tiles and "
+                            "at the level of fp32 FMA tiles; --tile-impl 7 = 4 planes / 30 bits)" if impl_used == 6 else
+                            "fp32 storage, vectors and epilogue; x_i.x_j through 4 int8 digit planes per operand (30 bits), 10 exact int32 tensor-core products recombined in fp64, rounded "
+                            "once to fp32" if impl_used == 7 else
                             "fp32 storage and accumulation; products via the 3xTF32 split on tcgen05 (error vs fp64 oracle ~2e-7, same as FFMA fp32)")),
         "matvecs_in_timed_region": int(tile_calls), "reference_cuda_baseline": ref_cuda, "fp64_dmma_tiles": dmma_line,
     }

@@ -52,7 +52,8 @@ typedef struct plssvm_b200_timings {
     double matvec_flops;      /* algorithmic FLOPs of ONE matvec: d * n * (n + 1)   */
     double h2d_bytes;
     double d2h_bytes;
-    int impl_used;            /* 1 = SIMT FMA tiles, 2 = tensor-core tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32), 3 = factorised linear */
+    int impl_used;            /* 1 = SIMT FMA tiles, 2 = floating-point tensor tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32), 3 = factorised linear,
+                               * 6 / 7 = int8-slice tcgen05 tiles (see "impl" below) */
     int reserved;
 } plssvm_b200_timings;
 
@@ -61,7 +62,11 @@ int plssvm_b200_create(int device, plssvm_b200_ctx **out);
 int plssvm_b200_destroy(plssvm_b200_ctx *ctx);
 /* message of the last failed call on this thread (valid until the next call) */
 const char *plssvm_b200_last_error(void);
-/* tuning / debugging knobs: "impl" (0 auto, 1 simt, 2 tensor), "check_interval" (CG iterations between host polls),
+/* tuning / debugging knobs: "impl" — tile kernel of the implicit matvec / predict contraction: 0 auto (int8-slice tcgen05 tiles;
+ * the floating-point tensor tiles for more than 16384 features or badly scaled rows), 1 SIMT FMA tiles, 2 floating-point tensor
+ * tiles (fp64: TMA + DMMA, fp32: tcgen05 3xTF32), 4 / 5 fp32 3xTF32 variants (CTA pair / 128x256), 6 int8 slices on tcgen05
+ * kind::i8 with exact int32 accumulation (fp64: 7 slices = 54 bits, fp32: 3 slices = 22 bits), 7 the same with 4 slices
+ * (30 bits) for fp32; "check_interval" (CG iterations between host polls),
  * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571), "linear_factorized" (0/1: for the linear kernel
  * evaluate Q~ v as X (X^T v) + rank-2 terms — two streaming passes over X, O(n d) instead of O(n^2 d); default 0 = the
  * implicit tiled formulation the reference uses), "ignore_convergence" (0/1, benchmarking only: the stopping test is

@@ -178,7 +178,7 @@ struct plssvm_b200_ctx {
     int rank = 0, world = 1;
     nccl_api::comm_t comm = nullptr;
     // options
-    int impl = 0;            // 0 auto, 1 simt, 2 tensor, 4 / 5 fp32 tcgen05 variants, 6 fp64 through int8 slices on tcgen05 (tile_i8.cuh)
+    int impl = 0;            // 0 auto, 1 simt, 2 tensor, 4 / 5 fp32 tcgen05 variants, 6 int8 slices on tcgen05 (tile_i8.cuh), 7 the same with the exact-input slice count
     int check_interval = 0;  // 0 = auto
     int verbose = 0;
     int ignore_convergence = 0;  // benchmarking: never set the convergence flag, so exactly the requested number of iterations runs
@@ -208,6 +208,7 @@ struct plssvm_b200_dataset {
     // created on first use by the int8-slice tensor path (impl 6): digit planes [S][N][ld8] (S = 7 for fp64, 4 for fp32) and row scales
     void *X_i8 = nullptr, *rscale = nullptr;
     std::size_t ld8 = 0;
+    int i8_slices = 0;    // number of digit planes X_i8 currently holds
     int i8_bad_rows = 0;  // rows whose elements are spread over too many orders of magnitude for the automatic choice (split_i8_kernel)
 };
 
@@ -276,26 +277,42 @@ void make_tensor_map_i8(plssvm_b200_ctx *ctx, CUtensorMap *tm, const std::int8_t
 
 inline std::size_t pitch_i8(const std::size_t d) { return (d + 127) / 128 * 128; }
 
-// rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold I8<T>::S * rows * ld8 bytes
+// number of int8 slices per operand for the tile-kernel choice `impl` (6: default, 7: exact-input count; the same for fp64)
 template <typename T>
-void run_split_i8(plssvm_b200_ctx *ctx, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8, T *rscale,
-                  int *bad_rows, cudaStream_t st) {
-    pb::split_i8_kernel<T><<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(X, rows, static_cast<std::uint32_t>(d), static_cast<std::uint32_t>(ld), planes, rows * ld8,
-                                                                                 static_cast<std::uint32_t>(ld8), rscale, bad_rows);
+int i8_slices_for(const int impl) { return impl == 7 ? pb::I8<T>::S_EXACT : pb::I8<T>::S; }
+
+// rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold slices * rows * ld8 bytes
+template <typename T>
+void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8,
+                  T *rscale, int *bad_rows, cudaStream_t st) {
+    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), ld8_32 = static_cast<std::uint32_t>(ld8);
+    if (slices == pb::I8<T>::S) {
+        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes, rows * ld8, ld8_32, rscale, bad_rows);
+    } else {
+        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes, rows * ld8, ld8_32, rscale, bad_rows);
+    }
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
 }
 
-// digit planes of a resident data set, created on first use
+// digit planes of a resident data set, created on first use (re-created when another slice count is asked for)
 template <typename T>
-void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
-    if (ds->X_i8 != nullptr) { return; }
+void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const int slices) {
+    if (ds->X_i8 != nullptr && ds->i8_slices == slices) { return; }
+    if (ds->X_i8 != nullptr) {
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        PB_CUDA(cudaFree(ds->X_i8));
+        PB_CUDA(cudaFree(ds->rscale));
+        ds->X_i8 = ds->rscale = nullptr;
+    }
     ds->ld8 = pitch_i8(ds->d);
-    PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(pb::I8<T>::S) * ds->N * ds->ld8));
+    PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(slices) * ds->N * ds->ld8));
     PB_CUDA(cudaMalloc(&ds->rscale, (ds->N + 2) * sizeof(T)));
+    ds->i8_slices = slices;
     int *bad_d = reinterpret_cast<int *>(static_cast<T *>(ds->rscale) + ds->N);  // scratch word behind the scales
     PB_CUDA(cudaMemsetAsync(bad_d, 0, sizeof(int), ctx->stream));
-    run_split_i8<T>(ctx, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<T *>(ds->rscale), bad_d, ctx->stream);
+    run_split_i8<T>(ctx, slices, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<T *>(ds->rscale), bad_d, ctx->stream);
     int *h = static_cast<int *>(ctx->pinned) + 512;  // second half of the pinned block (the first holds the CG state read-back)
     PB_CUDA(cudaMemcpyAsync(h, bad_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -315,21 +332,29 @@ void ensure_tf32_split(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
 }
 
 // automatic kernel choice only: the int8-slice tiles are used unless the data set holds badly scaled rows (split_i8_kernel)
-bool i8_allowed(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds) { return ctx->impl == 6 || ds->i8_bad_rows == 0; }
+bool i8_allowed(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds) { return ctx->impl == 6 || ctx->impl == 7 || ds->i8_bad_rows == 0; }
 
 template <typename T, int KERNEL, int MODE>
 void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
     const std::uint64_t ntiles = p.tile_hi - p.tile_lo;
     if (ntiles == 0) { return; }
     const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
-    if (impl == 6) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 4, units of 128 x 128)
-        using L8 = pb::I8Layout<T>;
+    if (impl == 6 || impl == 7) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 3 or 4, units of 128 x 128)
         PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
-        CUtensorMap tmA, tmB;
-        make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE), static_cast<std::uint32_t>(L8::S));
-        make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(L8::NH), static_cast<std::uint32_t>(L8::S));
-        PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_i8<T, KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
-        pb::tile_kernel_i8<T, KERNEL, MODE><<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+        auto launch = [&](auto slices) {
+            constexpr int S = decltype(slices)::value;
+            using L8 = pb::I8Layout<T, S>;
+            CUtensorMap tmA, tmB;
+            make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE), static_cast<std::uint32_t>(S));
+            make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(L8::NH), static_cast<std::uint32_t>(S));
+            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_i8<T, S, KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
+            pb::tile_kernel_i8<T, S, KERNEL, MODE><<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+        };
+        if (i8_slices_for<T>(impl) == pb::I8<T>::S) {
+            launch(std::integral_constant<int, pb::I8<T>::S>{});
+        } else {
+            launch(std::integral_constant<int, pb::I8<T>::S_EXACT>{});
+        }
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches++;
         return;
@@ -386,7 +411,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
     // int8-slice tcgen05 tiles: beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA / 3xTF32 tiles
-    if (ctx->impl == 6) { return features <= pb::I8_MAX_FEATURES ? 6 : 2; }
+    if (ctx->impl == 6 || ctx->impl == 7) { return features <= pb::I8_MAX_FEATURES ? (sizeof(T) == 8 ? 6 : ctx->impl) : 2; }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
     // auto: int8 slices on tcgen05 (tile_i8.cuh) where the int32 accumulators cannot overflow; callers fall back to 2 for badly scaled
@@ -436,8 +461,8 @@ struct matvec_plan {
         Tb = (n + TILE - 1) / TILE;
         const bool tiles_needed = !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR);
         impl = resolve_impl<T>(c, data->ld);
-        if (impl == 6 && tiles_needed) {
-            ensure_i8<T>(c, const_cast<plssvm_b200_dataset *>(data));
+        if ((impl == 6 || impl == 7) && tiles_needed) {
+            ensure_i8<T>(c, const_cast<plssvm_b200_dataset *>(data), i8_slices_for<T>(impl));
             if (!i8_allowed(c, data)) { impl = 2; }
         }
         if (sizeof(T) == 4 && tiles_needed && (impl == 2 || impl == 4 || impl == 5)) { ensure_tf32_split(c, const_cast<plssvm_b200_dataset *>(data)); }
@@ -449,7 +474,7 @@ struct matvec_plan {
         base.B = base.A;
         base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
         base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
-        if (impl == 6 && tiles_needed) {
+        if ((impl == 6 || impl == 7) && tiles_needed) {
             base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
             base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
             base.A_plane = base.B_plane = data->N * data->ld8;
@@ -803,7 +828,7 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
     if (impl == 4 || impl == 5) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
-    if (impl == 6) {
+    if (impl == 6 || impl == 7) {
         PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
         p.A_i8 = P_i8;
         p.A_scale = P_scale;
@@ -873,12 +898,12 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
     int impl = resolve_impl<T>(ctx, sv->ld);
-    if (impl == 6 && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
-        ensure_i8<T>(ctx, sv);
-        if (pts_ds != nullptr) { ensure_i8<T>(ctx, const_cast<plssvm_b200_dataset *>(pts_ds)); }
+    if ((impl == 6 || impl == 7) && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
+        ensure_i8<T>(ctx, sv, i8_slices_for<T>(impl));
+        if (pts_ds != nullptr) { ensure_i8<T>(ctx, const_cast<plssvm_b200_dataset *>(pts_ds), i8_slices_for<T>(impl)); }
         if (!i8_allowed(ctx, sv) || (pts_ds != nullptr && !i8_allowed(ctx, pts_ds))) { impl = 2; }
     }
-    const bool need_i8 = kernel != pb::K_LINEAR && impl == 6;
+    const bool need_i8 = kernel != pb::K_LINEAR && (impl == 6 || impl == 7);
     const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && (impl == 2 || impl == 4 || impl == 5);  // the 3xTF32 tcgen05 variants consume the hi / lo split
     if (need_split) {
         ensure_tf32_split(ctx, sv);
@@ -897,7 +922,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                 stage_lo[i] = workspace<T>(ctx, ctx_t::WS_LO0 + i, stage_rows * sv->ld);
             }
             if (need_i8) {
-                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8<T>::S) * stage_rows * ld8);
+                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8<T>::S_EXACT) * stage_rows * ld8);
                 stage_sc[i] = workspace<T>(ctx, ctx_t::WS_SC0 + i, stage_rows);
             }
             if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X[i], 0, stage_rows * sv->ld * sizeof(T), st)); }  // pad columns stay zero
@@ -951,7 +976,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                     }
                 }
                 if (need_i8) {
-                    run_split_i8<T>(ctx, stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], nullptr, st);
+                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], nullptr, st);
                     P_i8 = stage_i8[buf];
                     P_scale = stage_sc[buf];
                     P_plane = mb * ld8;
@@ -1123,8 +1148,9 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 5 || value == 6,
-                       "impl must be 0 (auto), 1 (simt), 2 (tensor), 4 (fp32: CTA-pair tensor), 5 (fp32: 128x256 tensor) or 6 (fp64: int8-slice tcgen05 tensor)");
+            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 5 || value == 6 || value == 7,
+                       "impl must be 0 (auto), 1 (simt), 2 (floating-point tensor tiles), 4 (fp32: CTA-pair 3xTF32), 5 (fp32: 128x256 3xTF32), 6 (int8-slice tcgen05 tiles) or "
+                       "7 (int8-slice tiles with the exact-input slice count: fp32 4 instead of 3 slices)");
             ctx->impl = static_cast<int>(value);
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");

@@ -1,6 +1,7 @@
 // Tile kernel of the implicit kernel matrix on the 5th-generation tensor cores for BOTH real types: tcgen05.mma kind::i8 over
 // int8 slices of X (an Ozaki-style error-free splitting), exact int32 accumulation in TMEM, fp64 recombination in the epilogue.
-// fp64: S = 7 slices (54 fractional bits), 128 x 64 units; fp32: S = 4 slices (30 bits — more than the 24 of the inputs), 128 x 128 units.
+// fp64: S = 7 slices (54 fractional bits), 128 x 64 units; fp32: S = 3 slices (22 bits, the input precision of the 3xTF32 scheme) or,
+// opt-in, S = 4 (30 bits — more than the 24 of the inputs), 128 x 128 units.
 //
 // Why: tcgen05.mma has no f64 kind and the FP64 pipes of B200 (DMMA == DFMA) stop at ~37 TFLOP/s; the int8 tensor pipe is
 // ~120x faster.  Every row x_i is written once per data set (split_i8_kernel) as a fixed-point number relative to its own
@@ -39,22 +40,25 @@ constexpr int I8_THREADS = 320;                            // producer warp, MMA
 constexpr int I8_EPI_THREADS = 256;
 constexpr std::uint32_t I8_TMEM_COLS = 512;
 constexpr std::uint32_t I8_MAX_FEATURES = 16384;           // <= 7 products of <= 2^14 per feature and diagonal stay below 2^31
-constexpr int I8_AUTO_MAX_RANGE = 20;                      // automatic choice: see split_i8_kernel (badly scaled rows -> DMMA tiles)
 
-// per real type: number of slices S (8 S - 2 fractional bits relative to the row maximum) and unit width NH (S * NH <= 512 TMEM columns)
+// per real type: default number of slices S (8 S - 2 fractional bits relative to the row maximum), unit width NH (S * NH <= 512 TMEM
+// columns) and the dynamic-range window of the automatic kernel choice (split_i8_kernel).
+//   fp64: S = 7 -> 54 bits (an fp64 input has 53)
+//   fp32: S = 3 -> 22 bits, the input precision of the 3xTF32 scheme (hi + lo = 2 x 11 bits) at 6 instead of 10 int8 products;
+//         S_EXACT = 4 -> 30 bits (every fp32 input within 2^6 of its row maximum is represented exactly), opt-in
 template <typename T>
 struct I8;
 template <>
 struct I8<double> {
-    static constexpr int S = 7, NH = 64;
+    static constexpr int S = 7, S_EXACT = 7, NH = 64, AUTO_RANGE = 20;
 };
 template <>
 struct I8<float> {
-    static constexpr int S = 4, NH = 128;
+    static constexpr int S = 3, S_EXACT = 4, NH = 128, AUTO_RANGE = 10;
 };
-template <typename T>
+template <typename T, int S_>
 struct I8Layout {
-    static constexpr int S = I8<T>::S, NH = I8<T>::NH;
+    static constexpr int S = S_, NH = I8<T>::NH;
     static constexpr int UNITS = TILE / NH;                     // units per 128 x 128 tile of the schedule
     static constexpr int A_SLICE = TILE * I8_BK;                // 8 KiB
     static constexpr int B_SLICE = NH * I8_BK;
@@ -75,14 +79,13 @@ struct I8Layout {
 // planes[p][row][k] (row pitch ld8 bytes, zero padded), rscale[row] = 2^(e_row - 6); one warp per row.
 // The products are accurate to ~2^-(8S-2) sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
 // which is at most the row norm), but elements far below their row's maximum keep fewer significant bits of their own.
-// bad_rows (optional) counts the rows where more than 1 / 16 of the non-zero elements lie more than 2^I8_AUTO_MAX_RANGE below the
-// largest one; the automatic kernel choice falls back to the DMMA tiles for such badly scaled fp64 data.
+// bad_rows (optional) counts the rows where more than 1 / 16 of the non-zero elements lie more than 2^AUTO_RANGE below the
+// largest one; the automatic kernel choice falls back to the floating-point tensor tiles (DMMA / 3xTF32) for such badly scaled data.
 // Rows containing inf / NaN get a NaN scale, so they poison their results exactly like native floating-point arithmetic would.
-template <typename T>
+template <typename T, int S>
 __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
                                                        std::int8_t *__restrict__ planes, const std::size_t plane_stride, const std::uint32_t ld8,
                                                        T *__restrict__ rscale, int *__restrict__ bad_rows) {
-    constexpr int S = I8<T>::S;
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) { return; }
     const int lane = threadIdx.x & 31;
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
     e = e < -900 ? -900 : e;
     if (sizeof(T) == 4) { e = e < -100 ? -100 : e; }  // keep the scale a normal float
     const double to_fixed = bad ? 0.0 : ldexp(1.0, (8 * S - 2) - e);
-    const double small = ldexp(1.0, e - I8_AUTO_MAX_RANGE);
+    const double small = ldexp(1.0, e - I8<T>::AUTO_RANGE);
     if (lane == 0) { rscale[row] = bad ? static_cast<T>(__longlong_as_double(0x7ff8000000000000ll)) : static_cast<T>(ldexp(1.0, e - 6)); }
     std::int8_t *out = planes + row * ld8;
     unsigned n_nonzero = 0, n_small = 0;
@@ -173,10 +176,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // exact int32 -> fp64 on the FP64 add pipe: (2^52 + 2^31 + a) - (2^52 + 2^31)
 __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __hiloint2double(0x43300000, static_cast<int>(a ^ 0x80000000u)) - 4503601774854144.0; }
 
-template <typename T, int KERNEL, int MODE>
+template <typename T, int S_, int KERNEL, int MODE>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<T> p) {
-    using L8 = I8Layout<T>;
+    using L8 = I8Layout<T, S_>;
     constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT;
     extern __shared__ unsigned char smem_raw[];
     if (p.done != nullptr && *p.done != 0) { return; }
