@@ -265,10 +265,10 @@ void make_tensor_map(plssvm_b200_ctx *ctx, CUtensorMap *tm, const T *base, const
 
 // 3-D map over the int8 digit planes [planes][rows][ld8]: box = 64 bytes x `box_rows` rows x all planes, 64-byte swizzle
 void make_tensor_map_i8(plssvm_b200_ctx *ctx, CUtensorMap *tm, const std::int8_t *base, const std::size_t rows, const std::size_t ld8, const std::size_t plane_bytes,
-                        const std::uint32_t box_rows, const std::uint32_t planes) {
+                        const std::uint32_t box_rows, const std::uint32_t planes, const std::uint32_t box_planes) {
     const cuuint64_t dims[3] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes) };
     const cuuint64_t strides[2] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(plane_bytes) };
-    const cuuint32_t box[3] = { static_cast<cuuint32_t>(pb::I8_BK), box_rows, planes };
+    const cuuint32_t box[3] = { static_cast<cuuint32_t>(pb::I8_BK), box_rows, box_planes };
     const cuuint32_t estr[3] = { 1, 1, 1 };
     const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<std::int8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                           CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -280,6 +280,10 @@ inline std::size_t pitch_i8(const std::size_t d) { return (d + 127) / 128 * 128;
 // number of int8 slices per operand for the tile-kernel choice `impl` (6: default, 7: exact-input count; the same for fp64)
 template <typename T>
 int i8_slices_for(const int impl) { return impl == 7 ? pb::I8<T>::S_EXACT : pb::I8<T>::S; }
+// int8-slice tile kernels: 6 default slice count, 7 exact-input slice count, 8 default slice count with 2 x 2 CTA clusters + TMA multicast
+inline bool is_i8(const int impl) { return impl == 6 || impl == 7 || impl == 8; }
+// kernels whose tile range / ownership is over 256 x 256 super-tiles
+inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8; }
 
 // rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold slices * rows * ld8 bytes
 template <typename T>
@@ -332,28 +336,54 @@ void ensure_tf32_split(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds) {
 }
 
 // automatic kernel choice only: the int8-slice tiles are used unless the data set holds badly scaled rows (split_i8_kernel)
-bool i8_allowed(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds) { return ctx->impl == 6 || ctx->impl == 7 || ds->i8_bad_rows == 0; }
+bool i8_allowed(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds) { return is_i8(ctx->impl) || ds->i8_bad_rows == 0; }
 
 template <typename T, int KERNEL, int MODE>
 void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
     const std::uint64_t ntiles = p.tile_hi - p.tile_lo;
     if (ntiles == 0) { return; }
     const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
-    if (impl == 6 || impl == 7) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 3 or 4, units of 128 x 128)
+    if (is_i8(impl)) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 3 or 4, units of 128 x 128)
         PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
-        auto launch = [&](auto slices) {
-            constexpr int S = decltype(slices)::value;
+        auto launch = [&](auto slices, auto cluster) {
+            constexpr int S = decltype(slices)::value, CL = decltype(cluster)::value;
             using L8 = pb::I8Layout<T, S>;
             CUtensorMap tmA, tmB;
-            make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE), static_cast<std::uint32_t>(S));
-            make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(L8::NH), static_cast<std::uint32_t>(S));
-            PB_CUDA(cudaFuncSetAttribute(pb::tile_kernel_i8<T, S, KERNEL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
-            pb::tile_kernel_i8<T, S, KERNEL, MODE><<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+            // CL = 1: one box = all planes of a row block; CL = 4: one plane per box (every CTA fetches every other plane and multicasts it)
+            make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE), static_cast<std::uint32_t>(S), CL == 1 ? static_cast<std::uint32_t>(S) : 1u);
+            make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(L8::NH), static_cast<std::uint32_t>(S), CL == 1 ? static_cast<std::uint32_t>(S) : 1u);
+            auto kern = pb::tile_kernel_i8<T, S, KERNEL, MODE, CL>;
+            PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
+            if constexpr (CL == 1) {
+                kern<<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+            } else {
+                cudaLaunchConfig_t cfg{};
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 4;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.blockDim = dim3(pb::I8_THREADS);
+                cfg.dynamicSmemBytes = L8::SMEM_BYTES;
+                cfg.stream = ctx->stream;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                cfg.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / 4 * 4));
+                int max_clusters = 0;  // clusters of four that can be resident at once (GPC boundaries can leave a few SMs unused)
+                PB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+                PB_REQUIRE(max_clusters > 0, "no 4-CTA cluster of the int8-slice kernel fits on this device");
+                const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(max_clusters)));
+                cfg.gridDim = dim3(4 * clusters);
+                PB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+            }
         };
-        if (i8_slices_for<T>(impl) == pb::I8<T>::S) {
-            launch(std::integral_constant<int, pb::I8<T>::S>{});
+        const bool dflt = i8_slices_for<T>(impl) == pb::I8<T>::S;
+        if (impl == 8) {
+            launch(std::integral_constant<int, pb::I8<T>::S>{}, std::integral_constant<int, 4>{});
+        } else if (dflt) {
+            launch(std::integral_constant<int, pb::I8<T>::S>{}, std::integral_constant<int, 1>{});
         } else {
-            launch(std::integral_constant<int, pb::I8<T>::S_EXACT>{});
+            launch(std::integral_constant<int, pb::I8<T>::S_EXACT>{}, std::integral_constant<int, 1>{});
         }
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches++;
@@ -411,7 +441,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
     // int8-slice tcgen05 tiles: beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA / 3xTF32 tiles
-    if (ctx->impl == 6 || ctx->impl == 7) { return features <= pb::I8_MAX_FEATURES ? (sizeof(T) == 8 ? 6 : ctx->impl) : 2; }
+    if (is_i8(ctx->impl)) { return features <= pb::I8_MAX_FEATURES ? ((sizeof(T) == 8 && ctx->impl == 7) ? 6 : ctx->impl) : 2; }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
     // auto: int8 slices on tcgen05 (tile_i8.cuh) where the int32 accumulators cannot overflow; callers fall back to 2 for badly scaled
@@ -461,12 +491,12 @@ struct matvec_plan {
         Tb = (n + TILE - 1) / TILE;
         const bool tiles_needed = !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR);
         impl = resolve_impl<T>(c, data->ld);
-        if ((impl == 6 || impl == 7) && tiles_needed) {
+        if (is_i8(impl) && tiles_needed) {
             ensure_i8<T>(c, const_cast<plssvm_b200_dataset *>(data), i8_slices_for<T>(impl));
             if (!i8_allowed(c, data)) { impl = 2; }
         }
         if (sizeof(T) == 4 && tiles_needed && (impl == 2 || impl == 4 || impl == 5)) { ensure_tf32_split(c, const_cast<plssvm_b200_dataset *>(data)); }
-        tile_shift = (impl == 4 || impl == 5) ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
+        tile_shift = super_tiled(impl) ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
         pb::rank_range(pb::tri_num_tiles((Tb + tile_shift) >> tile_shift), c->rank, c->world, tile_lo, tile_hi);
         if (tiles_needed) { partial.alloc(static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
@@ -474,7 +504,7 @@ struct matvec_plan {
         base.B = base.A;
         base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
         base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
-        if ((impl == 6 || impl == 7) && tiles_needed) {
+        if (is_i8(impl) && tiles_needed) {
             base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
             base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
             base.A_plane = base.B_plane = data->N * data->ld8;
@@ -827,8 +857,8 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
     p.T_cols = (p.n_cols + TILE - 1) / TILE;
     p.tile_lo = 0;
     p.tile_hi = static_cast<std::uint64_t>(p.T_rows) * p.T_cols;
-    if (impl == 4 || impl == 5) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
-    if (impl == 6 || impl == 7) {
+    if (super_tiled(impl)) { p.tile_hi = static_cast<std::uint64_t>((p.T_rows + 1) / 2) * ((p.T_cols + 1) / 2); }
+    if (is_i8(impl)) {
         PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
         p.A_i8 = P_i8;
         p.A_scale = P_scale;
@@ -898,12 +928,12 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     const std::size_t stage_rows = std::min(m, PREDICT_BATCH);
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
     int impl = resolve_impl<T>(ctx, sv->ld);
-    if ((impl == 6 || impl == 7) && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
+    if (is_i8(impl) && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
         ensure_i8<T>(ctx, sv, i8_slices_for<T>(impl));
         if (pts_ds != nullptr) { ensure_i8<T>(ctx, const_cast<plssvm_b200_dataset *>(pts_ds), i8_slices_for<T>(impl)); }
         if (!i8_allowed(ctx, sv) || (pts_ds != nullptr && !i8_allowed(ctx, pts_ds))) { impl = 2; }
     }
-    const bool need_i8 = kernel != pb::K_LINEAR && (impl == 6 || impl == 7);
+    const bool need_i8 = kernel != pb::K_LINEAR && is_i8(impl);
     const bool need_split = sizeof(T) == 4 && kernel != pb::K_LINEAR && (impl == 2 || impl == 4 || impl == 5);  // the 3xTF32 tcgen05 variants consume the hi / lo split
     if (need_split) {
         ensure_tf32_split(ctx, sv);
@@ -1148,9 +1178,9 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            PB_REQUIRE(value == 0 || value == 1 || value == 2 || value == 4 || value == 5 || value == 6 || value == 7,
+            PB_REQUIRE(value == 0 || value == 1 || value == 2 || (value >= 4 && value <= 8),
                        "impl must be 0 (auto), 1 (simt), 2 (floating-point tensor tiles), 4 (fp32: CTA-pair 3xTF32), 5 (fp32: 128x256 3xTF32), 6 (int8-slice tcgen05 tiles) or "
-                       "7 (int8-slice tiles with the exact-input slice count: fp32 4 instead of 3 slices)");
+                       "7 (int8-slice tiles with the exact-input slice count: fp32 4 instead of 3 slices), 8 (int8-slice tiles, 2 x 2 CTA clusters with TMA multicast)");
             ctx->impl = static_cast<int>(value);
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");

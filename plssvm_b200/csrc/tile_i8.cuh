@@ -32,6 +32,7 @@
 #include "common.cuh"
 #include "tile_dmma.cuh"  // mbarrier / TMA helpers
 #include "tile_tf32.cuh"  // tcgen05 helpers
+#include "tile_tf32_2sm.cuh"  // cluster helpers
 
 namespace pb {
 
@@ -166,6 +167,16 @@ __device__ __forceinline__ void tma_load_3d(const std::uint32_t dst, const CUten
                  ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
                  : "memory");
 }
+// the same load delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void tma_load_3d_mc(const std::uint32_t dst, const CUtensorMap *tm, const int c0, const int c1, const int c2, const std::uint32_t bar, const std::uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+                 : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(const std::uint32_t bar, const std::uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x8(const std::uint32_t taddr, std::uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -176,10 +187,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // exact int32 -> fp64 on the FP64 add pipe: (2^52 + 2^31 + a) - (2^52 + 2^31)
 __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __hiloint2double(0x43300000, static_cast<int>(a ^ 0x80000000u)) - 4503601774854144.0; }
 
-template <typename T, int S_, int KERNEL, int MODE>
+// CL = 1: one CTA per tile.  CL = 4: a cluster of 2 x 2 CTAs per 256 x 256 super-tile (launched with cluster dimension 4; the tile range is in
+// super-tiles like the CTA-pair 3xTF32 kernel's): CTA (r, c) computes tile (2 I2 + r, 2 J2 + c); the two CTAs of a cluster row need the same A
+// planes and the two of a cluster column the same B planes, so every CTA fetches only every other plane of its A block and of its B block and
+// TMA multicasts it to its mate — half the L2 -> SM traffic per CTA (the single-CTA kernel runs at 92 % of the L2 throughput cap).  A stage is
+// refilled once the MMA warps of all three CTAs that write into or read from it have released it (multicast tcgen05.commit, count 3).
+template <typename T, int S_, int KERNEL, int MODE, int CL>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<T> p) {
     using L8 = I8Layout<T, S_>;
+    static_assert(CL == 1 || CL == 4, "cluster size");
     constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT;
     extern __shared__ unsigned char smem_raw[];
     if (p.done != nullptr && *p.done != 0) { return; }
@@ -197,12 +214,38 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const std::uint32_t num_slabs = (p.ld8 + I8_BK - 1) / I8_BK;
+    std::uint32_t crank = 0;
+    if constexpr (CL == 4) { crank = cluster_ctarank(); }
+    const std::uint32_t cr = crank >> 1, cc = crank & 1u;  // position of this CTA inside the 2 x 2 cluster
+    const std::uint64_t work_first = (CL == 4) ? (blockIdx.x >> 2) : blockIdx.x, work_stride = (CL == 4) ? (gridDim.x >> 2) : gridDim.x;
+    const std::uint32_t S_rows = (p.T_rows + 1) >> 1, S_cols = (p.T_cols + 1) >> 1;
+    // work item L -> tile (I, J) of this CTA; `valid` = false for the padding / strictly-upper tile of a super-tile (computed, never stored)
+    auto decode = [&](const std::uint64_t L, std::uint32_t &I, std::uint32_t &J) -> bool {
+        if constexpr (CL == 1) {
+            if constexpr (MODE == MODE_SYM) {
+                tri_decode(p.T_rows, L, I, J);
+            } else {
+                rect_decode(p.T_rows, p.T_cols, L, I, J);
+            }
+            return true;
+        } else {
+            std::uint32_t I2, J2;
+            if constexpr (MODE == MODE_SYM) {
+                tri_decode(S_rows, L, I2, J2);
+            } else {
+                rect_decode(S_rows, S_cols, L, I2, J2);
+            }
+            I = 2 * I2 + cr;
+            J = 2 * J2 + cc;
+            return I < p.T_rows && J < p.T_cols && (MODE == MODE_RECT || J <= I);
+        }
+    };
 
     if (tid == 0) {
         #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, CL == 4 ? 3 : 1);  // CL = 4: this CTA's MMA warp, its row mate's and its column mate's
         }
         mbar_init(tfull, 1);
         mbar_init(tempty, I8_EPI_THREADS / 32);  // one arrive per epilogue warp
@@ -214,6 +257,7 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
+    if constexpr (CL == 4) { cluster_sync_all(); }  // the mbarriers of all four CTAs exist before anyone multicasts into them
     __syncthreads();
     tcgen05_fence_after();
     const std::uint32_t tmem_base = *tmem_slot;
@@ -222,13 +266,11 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             std::uint32_t stage = 0, phase = 0;
-            for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
+            const std::uint16_t mask_a = static_cast<std::uint16_t>(3u << (2 * cr));                // the two CTAs of this cluster row
+            const std::uint16_t mask_b = static_cast<std::uint16_t>((1u << cc) | (1u << (2 + cc)));  // the two CTAs of this cluster column
+            for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
                 std::uint32_t I, J;
-                if constexpr (MODE == MODE_SYM) {
-                    tri_decode(p.T_rows, L, I, J);
-                } else {
-                    rect_decode(p.T_rows, p.T_cols, L, I, J);
-                }
+                decode(L, I, J);
                 for (int h = 0; h < UNITS; ++h) {
                     const int ra = static_cast<int>(I * TILE), rb = static_cast<int>(J * TILE + h * NH);
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
@@ -236,8 +278,20 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const std::uint32_t dst = smem_u32(stages + stage * L8::STAGE_BYTES);
                         const std::uint32_t bar = full0 + 8 * stage;
                         mbar_arrive_expect_tx(bar, L8::STAGE_BYTES);
-                        tma_load_3d(dst, &tmA, static_cast<int>(ks * I8_BK), ra, 0, bar);
-                        tma_load_3d(dst + L8::A_BYTES, &tmB, static_cast<int>(ks * I8_BK), rb, 0, bar);
+                        if constexpr (CL == 1) {
+                            tma_load_3d(dst, &tmA, static_cast<int>(ks * I8_BK), ra, 0, bar);
+                            tma_load_3d(dst + L8::A_BYTES, &tmB, static_cast<int>(ks * I8_BK), rb, 0, bar);
+                        } else {
+                            // one plane per box: this CTA fetches every other plane of its row block / column block for itself and its mate
+                            #pragma unroll
+                            for (int pp = 0; pp < S; ++pp) {
+                                if ((pp & 1) == static_cast<int>(cc)) { tma_load_3d_mc(dst + pp * L8::A_SLICE, &tmA, static_cast<int>(ks * I8_BK), ra, pp, bar, mask_a); }
+                            }
+                            #pragma unroll
+                            for (int pp = 0; pp < S; ++pp) {
+                                if ((pp & 1) == static_cast<int>(cr)) { tma_load_3d_mc(dst + L8::A_BYTES + pp * L8::B_SLICE, &tmB, static_cast<int>(ks * I8_BK), rb, pp, bar, mask_b); }
+                            }
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -251,7 +305,8 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== MMA issuer =====
         if (lane == 0) {
             std::uint32_t stage = 0, phase = 0, unit_iter = 0;
-            for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
+            const std::uint16_t mask_rel = static_cast<std::uint16_t>((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));  // this CTA, its row mate, its column mate
+            for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
                 for (int h = 0; h < UNITS; ++h, ++unit_iter) {
                     mbar_wait(tempty, (unit_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous unit
                     tcgen05_fence_after();
@@ -277,7 +332,12 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 }
                             }
                         }
-                        umma_commit(empty0 + 8 * stage);  // smem stage reusable once these MMAs have read it
+                        // smem stage reusable once these MMAs have read it
+                        if constexpr (CL == 1) {
+                            umma_commit(empty0 + 8 * stage);
+                        } else {
+                            umma_commit_mc(empty0 + 8 * stage, mask_rel);
+                        }
                         if (++stage == STAGES) {
                             stage = 0;
                             phase ^= 1u;
@@ -295,13 +355,9 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = quarter * 32 + lane;   // accumulator row of this thread
         const int et = tid - 64;               // 0..255 among the epilogue threads
         std::uint32_t unit_iter = 0;
-        for (std::uint64_t L = p.tile_lo + blockIdx.x; L < p.tile_hi; L += gridDim.x) {
+        for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
             std::uint32_t I, J;
-            if constexpr (MODE == MODE_SYM) {
-                tri_decode(p.T_rows, L, I, J);
-            } else {
-                rect_decode(p.T_rows, p.T_cols, L, I, J);
-            }
+            const bool valid = decode(L, I, J);
             const std::uint32_t row0 = I * TILE;
             const bool diag = (MODE == MODE_SYM) && (I == J);
             const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
@@ -390,13 +446,13 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (h == UNITS - 1 && ch == 1) { s_rowsum[row] = rowacc; }
                 named_bar_sync(1, I8_EPI_THREADS);  // column sums of the four row quarters / row sums of the second column half visible
                 if constexpr (MODE == MODE_SYM) {
-                    if (!diag && et < NH) {
+                    if (!diag && valid && et < NH) {
                         const T s = ((s_colsum[et] + s_colsum[NH + et]) + s_colsum[2 * NH + et]) + s_colsum[3 * NH + et];
                         const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
                         p.partial[mslot * TILE + h * NH + et] = (col0 + et < p.n_cols) ? s : T(0);
                     }
                 }
-                if (h == UNITS - 1 && ch == 0) {
+                if (h == UNITS - 1 && ch == 0 && valid) {
                     const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
                     p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : T(0);
                 }
@@ -405,8 +461,9 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     }
 
-    // teardown: everyone done with TMEM before the allocating warp frees it
+    // teardown: everyone done with TMEM before the allocating warp frees it (CL = 4: and with each other's shared memory and mbarriers)
     tcgen05_fence_before();
+    if constexpr (CL == 4) { cluster_sync_all(); }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
