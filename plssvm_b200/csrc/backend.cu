@@ -205,8 +205,9 @@ struct plssvm_b200_dataset {
     void *X = nullptr;   // [N][ld]
     void *sq = nullptr;  // [N]
     void *X_hi = nullptr, *X_lo = nullptr;  // fp32 only: TF32 hi / lo split of X for the 3xTF32 tensor path
-    // created on first use by the int8-slice tensor path (impl 6): digit planes [S][N][ld8] (S = 7 for fp64, 4 for fp32) and row scales
-    void *X_i8 = nullptr, *rscale = nullptr;
+    // created on first use by the int8-slice tensor path (impl 6): digit planes in the boxed layout of split_i8_kernel — X_i8 with boxes of 128 rows
+    // (A operand), X_i8b with boxes of NH rows (B operand; the same buffer when NH = 128, i.e. fp32) — and the row scales
+    void *X_i8 = nullptr, *X_i8b = nullptr, *rscale = nullptr;
     std::size_t ld8 = 0;
     int i8_slices = 0;    // number of digit planes X_i8 currently holds
     int i8_bad_rows = 0;  // rows whose elements are spread over too many orders of magnitude for the automatic choice (split_i8_kernel)
@@ -263,19 +264,9 @@ void make_tensor_map(plssvm_b200_ctx *ctx, CUtensorMap *tm, const T *base, const
     if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(rc))); }
 }
 
-// 3-D map over the int8 digit planes [planes][rows][ld8]: box = 64 bytes x `box_rows` rows x all planes, 64-byte swizzle
-void make_tensor_map_i8(plssvm_b200_ctx *ctx, CUtensorMap *tm, const std::int8_t *base, const std::size_t rows, const std::size_t ld8, const std::size_t plane_bytes,
-                        const std::uint32_t box_rows, const std::uint32_t planes, const std::uint32_t box_planes) {
-    const cuuint64_t dims[3] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes) };
-    const cuuint64_t strides[2] = { static_cast<cuuint64_t>(ld8), static_cast<cuuint64_t>(plane_bytes) };
-    const cuuint32_t box[3] = { static_cast<cuuint32_t>(pb::I8_BK), box_rows, box_planes };
-    const cuuint32_t estr[3] = { 1, 1, 1 };
-    const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<std::int8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes) failed with code " + std::to_string(static_cast<int>(rc))); }
-}
-
-inline std::size_t pitch_i8(const std::size_t d) { return (d + 127) / 128 * 128; }
+// int8 digit planes (tile_i8.cuh): features padded to whole 64-byte slabs, rows to whole 128-row boxes
+inline std::size_t pitch_i8(const std::size_t d) { return (d + 63) / 64 * 64; }
+inline std::size_t rows_i8(const std::size_t rows) { return (rows + 127) / 128 * 128; }
 
 // number of int8 slices per operand for the tile-kernel choice `impl` (6: default, 7: exact-input count; the same for fp64)
 template <typename T>
@@ -285,16 +276,19 @@ inline bool is_i8(const int impl) { return impl == 6 || impl == 7 || impl == 8; 
 // kernels whose tile range / ownership is over 256 x 256 super-tiles
 inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8; }
 
-// rows -> int8 digit planes + row scales (tile_i8.cuh); planes must hold slices * rows * ld8 bytes
+// rows -> int8 digit planes + row scales (tile_i8.cuh); planes_a / planes_b (the same buffer for fp32) hold slices * rows_i8(rows) * ld8 bytes each
 template <typename T>
-void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes, const std::size_t ld8,
-                  T *rscale, int *bad_rows, cudaStream_t st) {
+void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes_a,
+                  std::int8_t *planes_b, const std::size_t ld8, T *rscale, int *bad_rows, cudaStream_t st) {
+    const std::size_t bytes = static_cast<std::size_t>(slices) * rows_i8(rows) * ld8;
+    PB_CUDA(cudaMemsetAsync(planes_a, 0, bytes, st));  // padding rows / features are zero
+    if (planes_b != planes_a) { PB_CUDA(cudaMemsetAsync(planes_b, 0, bytes, st)); }
     const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-    const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), ld8_32 = static_cast<std::uint32_t>(ld8);
+    const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), slabs = static_cast<std::uint32_t>(ld8 / 64);
     if (slices == pb::I8<T>::S) {
-        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes, rows * ld8, ld8_32, rscale, bad_rows);
+        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, slabs, rscale, bad_rows);
     } else {
-        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes, rows * ld8, ld8_32, rscale, bad_rows);
+        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, slabs, rscale, bad_rows);
     }
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
@@ -306,17 +300,22 @@ void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const int slices) 
     if (ds->X_i8 != nullptr && ds->i8_slices == slices) { return; }
     if (ds->X_i8 != nullptr) {
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ds->X_i8b != ds->X_i8) { PB_CUDA(cudaFree(ds->X_i8b)); }
         PB_CUDA(cudaFree(ds->X_i8));
         PB_CUDA(cudaFree(ds->rscale));
-        ds->X_i8 = ds->rscale = nullptr;
+        ds->X_i8 = ds->X_i8b = ds->rscale = nullptr;
     }
     ds->ld8 = pitch_i8(ds->d);
-    PB_CUDA(cudaMalloc(&ds->X_i8, static_cast<std::size_t>(slices) * ds->N * ds->ld8));
+    const std::size_t plane_bytes = static_cast<std::size_t>(slices) * rows_i8(ds->N) * ds->ld8;
+    PB_CUDA(cudaMalloc(&ds->X_i8, plane_bytes));
+    ds->X_i8b = ds->X_i8;
+    if (pb::I8<T>::NH != TILE) { PB_CUDA(cudaMalloc(&ds->X_i8b, plane_bytes)); }
     PB_CUDA(cudaMalloc(&ds->rscale, (ds->N + 2) * sizeof(T)));
     ds->i8_slices = slices;
     int *bad_d = reinterpret_cast<int *>(static_cast<T *>(ds->rscale) + ds->N);  // scratch word behind the scales
     PB_CUDA(cudaMemsetAsync(bad_d, 0, sizeof(int), ctx->stream));
-    run_split_i8<T>(ctx, slices, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), ds->ld8, static_cast<T *>(ds->rscale), bad_d, ctx->stream);
+    run_split_i8<T>(ctx, slices, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), static_cast<std::int8_t *>(ds->X_i8b), ds->ld8,
+                    static_cast<T *>(ds->rscale), bad_d, ctx->stream);
     int *h = static_cast<int *>(ctx->pinned) + 512;  // second half of the pinned block (the first holds the CG state read-back)
     PB_CUDA(cudaMemcpyAsync(h, bad_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -348,14 +347,10 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
         auto launch = [&](auto slices, auto cluster) {
             constexpr int S = decltype(slices)::value, CL = decltype(cluster)::value;
             using L8 = pb::I8Layout<T, S>;
-            CUtensorMap tmA, tmB;
-            // CL = 1: one box = all planes of a row block; CL = 4: one plane per box (every CTA fetches every other plane and multicasts it)
-            make_tensor_map_i8(ctx, &tmA, p.A_i8, p.n_rows, p.ld8, p.A_plane, static_cast<std::uint32_t>(TILE), static_cast<std::uint32_t>(S), CL == 1 ? static_cast<std::uint32_t>(S) : 1u);
-            make_tensor_map_i8(ctx, &tmB, p.B_i8, p.n_cols, p.ld8, p.B_plane, static_cast<std::uint32_t>(L8::NH), static_cast<std::uint32_t>(S), CL == 1 ? static_cast<std::uint32_t>(S) : 1u);
             auto kern = pb::tile_kernel_i8<T, S, KERNEL, MODE, CL>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
             if constexpr (CL == 1) {
-                kern<<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+                kern<<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(p);
             } else {
                 cudaLaunchConfig_t cfg{};
                 cudaLaunchAttribute attr[1];
@@ -374,7 +369,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
                 PB_REQUIRE(max_clusters > 0, "no 4-CTA cluster of the int8-slice kernel fits on this device");
                 const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(max_clusters)));
                 cfg.gridDim = dim3(4 * clusters);
-                PB_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+                PB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
             }
         };
         const bool dflt = i8_slices_for<T>(impl) == pb::I8<T>::S;
@@ -505,9 +500,9 @@ struct matvec_plan {
         base.A_hi = base.B_hi = static_cast<const T *>(data->X_hi);
         base.A_lo = base.B_lo = static_cast<const T *>(data->X_lo);
         if (is_i8(impl) && tiles_needed) {
-            base.A_i8 = base.B_i8 = static_cast<const std::int8_t *>(data->X_i8);
+            base.A_i8 = static_cast<const std::int8_t *>(data->X_i8);
+            base.B_i8 = static_cast<const std::int8_t *>(data->X_i8b);
             base.A_scale = base.B_scale = static_cast<const T *>(data->rscale);
-            base.A_plane = base.B_plane = data->N * data->ld8;
             base.ld8 = static_cast<std::uint32_t>(data->ld8);
         }
         base.n_rows = n;
@@ -643,6 +638,7 @@ plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const T *X, const std:
         cudaFree(ds->sq);
         cudaFree(ds->X_hi);
         cudaFree(ds->X_lo);
+        if (ds->X_i8b != ds->X_i8) { cudaFree(ds->X_i8b); }
         cudaFree(ds->X_i8);
         cudaFree(ds->rscale);
         delete ds;
@@ -834,7 +830,7 @@ void run_w_kernel(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *
 // points: `pts` rows [p0, p0 + m) of a resident matrix; out_d: m values on the device
 template <typename T>
 void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, const T *alpha_d, const T *w_d, const T rho, const T *P, const T *P_sq, const T *P_hi,
-                         const T *P_lo, const std::int8_t *P_i8, const T *P_scale, const std::size_t P_plane, const std::size_t m, const KernelParams<T> &kp, const int impl,
+                         const T *P_lo, const std::int8_t *P_i8, const T *P_scale, const std::size_t m, const KernelParams<T> &kp, const int impl,
                          T *out_d) {
     const std::uint32_t ld = static_cast<std::uint32_t>(sv->ld);
     if (kp.kernel == pb::K_LINEAR) {
@@ -862,10 +858,8 @@ void predict_rows_device(plssvm_b200_ctx *ctx, const plssvm_b200_dataset *sv, co
         PB_REQUIRE(P_i8 != nullptr && P_scale != nullptr, "int8-slice tensor path needs the digit planes of the predict points");
         p.A_i8 = P_i8;
         p.A_scale = P_scale;
-        p.A_plane = P_plane;
-        p.B_i8 = static_cast<const std::int8_t *>(sv->X_i8);
+        p.B_i8 = static_cast<const std::int8_t *>(sv->X_i8b);
         p.B_scale = static_cast<const T *>(sv->rscale);
-        p.B_plane = sv->N * sv->ld8;
         p.ld8 = static_cast<std::uint32_t>(sv->ld8);
     }
     p.row_sq = P_sq;
@@ -952,7 +946,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                 stage_lo[i] = workspace<T>(ctx, ctx_t::WS_LO0 + i, stage_rows * sv->ld);
             }
             if (need_i8) {
-                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8<T>::S_EXACT) * stage_rows * ld8);
+                stage_i8[i] = workspace<std::int8_t>(ctx, ctx_t::WS_I8_0 + i, static_cast<std::size_t>(pb::I8<T>::S_EXACT) * rows_i8(stage_rows) * ld8);
                 stage_sc[i] = workspace<T>(ctx, ctx_t::WS_SC0 + i, stage_rows);
             }
             if (sv->ld != sv->d) { PB_CUDA(cudaMemsetAsync(stage_X[i], 0, stage_rows * sv->ld * sizeof(T), st)); }  // pad columns stay zero
@@ -971,14 +965,12 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
             const T *P_hi = nullptr, *P_lo = nullptr;
             const std::int8_t *P_i8 = nullptr;
             const T *P_scale = nullptr;
-            std::size_t P_plane = 0;
             if (pts_ds != nullptr) {
                 P = static_cast<const T *>(pts_ds->X) + p0 * pts_ds->ld;
                 P_sq = static_cast<const T *>(pts_ds->sq) + p0;
                 if (need_i8) {
-                    P_i8 = static_cast<const std::int8_t *>(pts_ds->X_i8) + p0 * pts_ds->ld8;
+                    P_i8 = static_cast<const std::int8_t *>(pts_ds->X_i8) + p0 * pts_ds->ld8 * static_cast<std::size_t>(pts_ds->i8_slices);  // p0 is a multiple of 128 rows: whole boxes
                     P_scale = static_cast<const T *>(pts_ds->rscale) + p0;
-                    P_plane = pts_ds->N * pts_ds->ld8;
                 }
                 if (pts_ds->X_hi != nullptr) {
                     P_hi = static_cast<const T *>(pts_ds->X_hi) + p0 * pts_ds->ld;
@@ -1006,17 +998,16 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                     }
                 }
                 if (need_i8) {
-                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], ld8, stage_sc[buf], nullptr, st);
+                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], stage_i8[buf], ld8, stage_sc[buf], nullptr, st);  // A operand only
                     P_i8 = stage_i8[buf];
                     P_scale = stage_sc[buf];
-                    P_plane = mb * ld8;
                 }
                 P = stage_X[buf];
                 P_sq = stage_sq[buf];
                 P_hi = stage_hi[buf];
                 P_lo = stage_lo[buf];
             }
-            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, P_i8, P_scale, P_plane, mb, kp, impl, out_d + (p0 - s0));
+            predict_rows_device<T>(ctx, sv, alpha_d, w_d, shift_rho, P, P_sq, P_hi, P_lo, P_i8, P_scale, mb, kp, impl, out_d + (p0 - s0));
             if (pts_ds == nullptr) { PB_CUDA(cudaEventRecord(ctx->ev_computed[batch_index & 1], st)); }
         }
         PB_CUDA(cudaMemcpyAsync(out + s0, out_d, ms * sizeof(T), cudaMemcpyDeviceToHost, st));
@@ -1248,6 +1239,7 @@ int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
         cudaFree(ds->sq);
         cudaFree(ds->X_hi);
         cudaFree(ds->X_lo);
+        if (ds->X_i8b != ds->X_i8) { cudaFree(ds->X_i8b); }
         cudaFree(ds->X_i8);
         cudaFree(ds->rscale);
         delete ds;

@@ -32,11 +32,11 @@ struct TileParams {
     const T *B;
     const T *A_hi, *A_lo;  // fp32 tensor path only: TF32 hi / lo split of A and B (tile_tf32.cuh)
     const T *B_hi, *B_lo;
-    // fp64 int8-slice tensor path only (tile_i8.cuh): digit planes [S][rows][ld8] of A and B and the per-row scales 2^(e - 6)
+    // int8-slice tensor path only (tile_i8.cuh): digit planes of A (boxes of 128 rows) and B (boxes of NH rows) in the boxed, pre-swizzled
+    // layout of split_i8_kernel, and the per-row scales 2^(e - 6)
     const std::int8_t *A_i8, *B_i8;
     const T *A_scale, *B_scale;
-    std::uint64_t A_plane, B_plane;  // bytes between two digit planes
-    std::uint32_t ld8;               // row pitch of the digit planes in bytes
+    std::uint32_t ld8;               // features padded to a multiple of 64 (= 64 x number of slabs)
     std::uint32_t n_rows;  // valid rows of A  (SYM: n = N - 1)
     std::uint32_t n_cols;  // valid rows of B
     std::uint32_t ld;      // row pitch in elements (multiple of 128 bytes, zero padded)

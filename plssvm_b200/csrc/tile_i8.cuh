@@ -18,8 +18,8 @@
 // slice A_p with the m consecutive slices B_q .. B_(q+m-1) and lands in the m consecutive accumulators t' .. t'+m-1:
 // 10 wide MMAs (N up to 256) per 32-feature step instead of 28 narrow ones, which cuts the shared-memory operand traffic
 // from 168 KB to 96 KB per step (107 B/clk at the tensor pipe's pace — under the 128 B/clk the SM can deliver).
-//   * warp 0: TMA producer — per 64-feature slab two 3-D boxes {64 B, rows, S slices}, SWIZZLE_64B: A = 128 rows (56 KB),
-//     B = 64 rows (28 KB); 2-stage ring
+//   * warp 0: producer — per 64-feature slab two contiguous bulk copies (cp.async.bulk) of pre-swizzled operand boxes: A = 128 rows x S planes
+//     (56 KB), B = 64 rows x S planes (28 KB); 2-stage ring (see split_i8_kernel for the layout in HBM)
 //   * warp 1: allocates all 512 TMEM columns (S x 64 int32 accumulator columns) and issues the MMAs from one elected lane
 //   * warps 2-9: epilogue, one accumulator row and 32 columns per thread: tcgen05.ld, int32 -> fp64 without I2F (exponent
 //     trick), Horner recombination, hand TMEM back to the MMA warp, then kernel function, QA_cost - q_i - q_j (+ 1/C on the
@@ -77,15 +77,28 @@ struct I8Layout {
 };
 
 // ---- operand preparation: rows -> S int8 digit planes + per-row scale ---------------------------------------------------------
-// planes[p][row][k] (row pitch ld8 bytes, zero padded), rscale[row] = 2^(e_row - 6); one warp per row.
+// Layout of the planes in HBM ("boxed", pre-swizzled): the operand boxes the tile kernel stages are stored as CONTIGUOUS chunks that already
+// are the shared-memory image tcgen05.mma expects (K-major, 64-byte rows, SWIZZLE_64B), so the producer fetches them with plain 1-D bulk
+// copies (cp.async.bulk, whole 128-byte lines) instead of 2-D / 3-D tensor boxes whose 64-byte rows halve TMA's request efficiency:
+//     box(R, ks) = all S planes of the BR rows [R BR, (R+1) BR) and the 64 features [64 ks, 64 ks + 64):  S x BR x 64 bytes, plane-major;
+//     offset(p, r, k) = (((r / BR) num_slabs + k / 64) S + p) BR 64 + (r % BR) 64 + ((((k % 64) / 16) ^ (((r % BR) / 2) % 4)) 16) + k % 16
+// The A operand (tile rows) uses BR = 128; the B operand (unit columns) BR = NH (fp64: 64 — a second copy; fp32: 128 — the same buffer).
+// Rows are padded to a multiple of 128 and features to a multiple of 64 with zeros (the buffers are cleared before the split).
+// rscale[row] = 2^(e_row - 6); one warp per row.
 // The products are accurate to ~2^-(8S-2) sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
 // which is at most the row norm), but elements far below their row's maximum keep fewer significant bits of their own.
 // bad_rows (optional) counts the rows where more than 1 / 16 of the non-zero elements lie more than 2^AUTO_RANGE below the
 // largest one; the automatic kernel choice falls back to the floating-point tensor tiles (DMMA / 3xTF32) for such badly scaled data.
 // Rows containing inf / NaN get a NaN scale, so they poison their results exactly like native floating-point arithmetic would.
+__host__ __device__ __forceinline__ std::size_t i8_boxed_offset(const std::size_t r, const std::uint32_t k, const std::uint32_t p, const std::uint32_t S, const std::uint32_t BR,
+                                                                 const std::uint32_t num_slabs) {
+    const std::uint32_t rr = static_cast<std::uint32_t>(r % BR), kk = k & 63u;
+    return (((r / BR) * num_slabs + (k >> 6)) * S + p) * (static_cast<std::size_t>(BR) * 64u) + rr * 64u + ((((kk >> 4) ^ ((rr >> 1) & 3u)) << 4) | (kk & 15u));
+}
+
 template <typename T, int S>
 __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
-                                                       std::int8_t *__restrict__ planes, const std::size_t plane_stride, const std::uint32_t ld8,
+                                                       std::int8_t *__restrict__ planes_a, std::int8_t *__restrict__ planes_b, const std::uint32_t num_slabs,
                                                        T *__restrict__ rscale, int *__restrict__ bad_rows) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) { return; }
@@ -111,9 +124,8 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
     const double to_fixed = bad ? 0.0 : ldexp(1.0, (8 * S - 2) - e);
     const double small = ldexp(1.0, e - I8<T>::AUTO_RANGE);
     if (lane == 0) { rscale[row] = bad ? static_cast<T>(__longlong_as_double(0x7ff8000000000000ll)) : static_cast<T>(ldexp(1.0, e - 6)); }
-    std::int8_t *out = planes + row * ld8;
     unsigned n_nonzero = 0, n_small = 0;
-    for (std::uint32_t k0 = 4u * lane; k0 < ld8; k0 += 128u) {
+    for (std::uint32_t k0 = 4u * lane; k0 < 64u * num_slabs; k0 += 128u) {
         long long v[4];
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -131,7 +143,8 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
                 word |= (static_cast<std::uint32_t>(a) & 0xFFu) << (8 * j);
                 v[j] = (v[j] - a) >> 8;  // exact
             }
-            *reinterpret_cast<std::uint32_t *>(out + static_cast<std::size_t>(p) * plane_stride + k0) = word;
+            *reinterpret_cast<std::uint32_t *>(planes_a + i8_boxed_offset(row, k0, p, S, TILE, num_slabs)) = word;
+            if (planes_b != planes_a) { *reinterpret_cast<std::uint32_t *>(planes_b + i8_boxed_offset(row, k0, p, S, I8<T>::NH, num_slabs)) = word; }
         }
     }
     if (bad_rows != nullptr) {
@@ -162,15 +175,14 @@ __device__ __forceinline__ void umma_i8(const std::uint32_t tmem_d, const std::u
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(const std::uint32_t dst, const CUtensorMap *tm, const int c0, const int c1, const int c2, const std::uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
-                 : "memory");
+// contiguous global -> shared bulk copy (TMA engine, SASS UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(const std::uint32_t dst, const void *src, const std::uint32_t bytes, const std::uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// the same load delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in `mask`
-__device__ __forceinline__ void tma_load_3d_mc(const std::uint32_t dst, const CUtensorMap *tm, const int c0, const int c1, const int c2, const std::uint32_t bar, const std::uint16_t mask) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
-                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+// the same copy delivered to the same shared-memory offset (and mbarrier) of every CTA of the cluster named in `mask`
+__device__ __forceinline__ void bulk_load_mc(const std::uint32_t dst, const void *src, const std::uint32_t bytes, const std::uint32_t bar, const std::uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "h"(mask)
                  : "memory");
 }
 // tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
@@ -194,7 +206,7 @@ __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __h
 // refilled once the MMA warps of all three CTAs that write into or read from it have released it (multicast tcgen05.commit, count 3).
 template <typename T, int S_, int KERNEL, int MODE, int CL>
 __global__ void __launch_bounds__(I8_THREADS, 1)
-tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<T> p) {
+tile_kernel_i8(const TileParams<T> p) {
     using L8 = I8Layout<T, S_>;
     static_assert(CL == 1 || CL == 4, "cluster size");
     constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT;
@@ -213,7 +225,7 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const std::uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const std::uint32_t num_slabs = (p.ld8 + I8_BK - 1) / I8_BK;
+    const std::uint32_t num_slabs = p.ld8 / I8_BK;
     std::uint32_t crank = 0;
     if constexpr (CL == 4) { crank = cluster_ctarank(); }
     const std::uint32_t cr = crank >> 1, cc = crank & 1u;  // position of this CTA inside the 2 x 2 cluster
@@ -271,25 +283,32 @@ tile_kernel_i8(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
                 std::uint32_t I, J;
                 decode(L, I, J);
+                // padding tiles of a super-tile (CL = 4, odd tile counts) load the last valid block instead of running past the buffers
+                const std::uint32_t Il = I < p.T_rows ? I : p.T_rows - 1, Jl = J < p.T_cols ? J : p.T_cols - 1;
                 for (int h = 0; h < UNITS; ++h) {
-                    const int ra = static_cast<int>(I * TILE), rb = static_cast<int>(J * TILE + h * NH);
+                    const std::int8_t *src_a = p.A_i8 + static_cast<std::size_t>(Il) * num_slabs * L8::A_BYTES;
+                    const std::int8_t *src_b = p.B_i8 + (static_cast<std::size_t>(Jl) * UNITS + h) * num_slabs * L8::B_BYTES;
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1u);
                         const std::uint32_t dst = smem_u32(stages + stage * L8::STAGE_BYTES);
                         const std::uint32_t bar = full0 + 8 * stage;
                         mbar_arrive_expect_tx(bar, L8::STAGE_BYTES);
                         if constexpr (CL == 1) {
-                            tma_load_3d(dst, &tmA, static_cast<int>(ks * I8_BK), ra, 0, bar);
-                            tma_load_3d(dst + L8::A_BYTES, &tmB, static_cast<int>(ks * I8_BK), rb, 0, bar);
+                            bulk_load(dst, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES, L8::A_BYTES, bar);
+                            bulk_load(dst + L8::A_BYTES, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES, L8::B_BYTES, bar);
                         } else {
-                            // one plane per box: this CTA fetches every other plane of its row block / column block for itself and its mate
+                            // this CTA fetches every other plane of its row block / column block for itself and its mate
                             #pragma unroll
                             for (int pp = 0; pp < S; ++pp) {
-                                if ((pp & 1) == static_cast<int>(cc)) { tma_load_3d_mc(dst + pp * L8::A_SLICE, &tmA, static_cast<int>(ks * I8_BK), ra, pp, bar, mask_a); }
+                                if ((pp & 1) == static_cast<int>(cc)) {
+                                    bulk_load_mc(dst + pp * L8::A_SLICE, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES + pp * L8::A_SLICE, L8::A_SLICE, bar, mask_a);
+                                }
                             }
                             #pragma unroll
                             for (int pp = 0; pp < S; ++pp) {
-                                if ((pp & 1) == static_cast<int>(cr)) { tma_load_3d_mc(dst + L8::A_BYTES + pp * L8::B_SLICE, &tmB, static_cast<int>(ks * I8_BK), rb, pp, bar, mask_b); }
+                                if ((pp & 1) == static_cast<int>(cr)) {
+                                    bulk_load_mc(dst + L8::A_BYTES + pp * L8::B_SLICE, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES + pp * L8::B_SLICE, L8::B_SLICE, bar, mask_b);
+                                }
                             }
                         }
                         if (++stage == STAGES) {
