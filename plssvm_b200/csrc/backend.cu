@@ -280,10 +280,7 @@ inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl 
 template <typename T>
 void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes_a,
                   std::int8_t *planes_b, const std::size_t ld8, T *rscale, int *bad_rows, cudaStream_t st) {
-    const std::size_t bytes = static_cast<std::size_t>(slices) * rows_i8(rows) * ld8;
-    PB_CUDA(cudaMemsetAsync(planes_a, 0, bytes, st));  // padding rows / features are zero
-    if (planes_b != planes_a) { PB_CUDA(cudaMemsetAsync(planes_b, 0, bytes, st)); }
-    const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+    const unsigned grid = static_cast<unsigned>(rows_i8(rows) / 8);  // incl. the padding rows of the last box, which get zero digits
     const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), slabs = static_cast<std::uint32_t>(ld8 / 64);
     if (slices == pb::I8<T>::S) {
         pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, slabs, rscale, bad_rows);

@@ -83,7 +83,7 @@ struct I8Layout {
 //     box(R, ks) = all S planes of the BR rows [R BR, (R+1) BR) and the 64 features [64 ks, 64 ks + 64):  S x BR x 64 bytes, plane-major;
 //     offset(p, r, k) = (((r / BR) num_slabs + k / 64) S + p) BR 64 + (r % BR) 64 + ((((k % 64) / 16) ^ (((r % BR) / 2) % 4)) 16) + k % 16
 // The A operand (tile rows) uses BR = 128; the B operand (unit columns) BR = NH (fp64: 64 — a second copy; fp32: 128 — the same buffer).
-// Rows are padded to a multiple of 128 and features to a multiple of 64 with zeros (the buffers are cleared before the split).
+// Rows are padded to a multiple of 128 and features to a multiple of 64 with zero digits (written by this kernel: launch it over the padded rows).
 // rscale[row] = 2^(e_row - 6); one warp per row.
 // The products are accurate to ~2^-(8S-2) sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
 // which is at most the row norm), but elements far below their row's maximum keep fewer significant bits of their own.
@@ -101,11 +101,12 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
                                                        std::int8_t *__restrict__ planes_a, std::int8_t *__restrict__ planes_b, const std::uint32_t num_slabs,
                                                        T *__restrict__ rscale, int *__restrict__ bad_rows) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) { return; }
+    if (row >= (rows + TILE - 1) / TILE * TILE) { return; }
+    const bool pad_row = row >= rows;  // padding rows of the last 128-row box: all digits zero
     const int lane = threadIdx.x & 31;
-    const T *x = X + row * ld;
+    const T *x = X + (pad_row ? 0 : row) * ld;
     double mx = 0.0, poison = 0.0;
-    for (std::uint32_t k = lane; k < d; k += 32) {
+    for (std::uint32_t k = lane; k < (pad_row ? 0u : d); k += 32) {
         const double ax = fabs(static_cast<double>(x[k]));
         mx = fmax(mx, ax);
         poison += ax * 0.0;  // NaN iff the row holds an inf or a NaN
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
         mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         poison += __shfl_xor_sync(0xffffffffu, poison, o);
     }
-    const bool bad = poison != 0.0 || mx > 1.0e300;  // (poison is 0 or NaN)
+    const bool bad = poison != 0.0 || mx > 1.0e300 || pad_row;  // (poison is 0 or NaN)
     if (bad) { mx = 0.0; }
     int e = 0;
     if (mx > 0.0) { (void) frexp(mx, &e); }  // mx = m 2^e, m in [0.5, 1)  =>  |x_k| < 2^e
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
     if (sizeof(T) == 4) { e = e < -100 ? -100 : e; }  // keep the scale a normal float
     const double to_fixed = bad ? 0.0 : ldexp(1.0, (8 * S - 2) - e);
     const double small = ldexp(1.0, e - I8<T>::AUTO_RANGE);
-    if (lane == 0) { rscale[row] = bad ? static_cast<T>(__longlong_as_double(0x7ff8000000000000ll)) : static_cast<T>(ldexp(1.0, e - 6)); }
+    if (lane == 0 && !pad_row) { rscale[row] = bad ? static_cast<T>(__longlong_as_double(0x7ff8000000000000ll)) : static_cast<T>(ldexp(1.0, e - 6)); }
     unsigned n_nonzero = 0, n_small = 0;
     for (std::uint32_t k0 = 4u * lane; k0 < 64u * num_slabs; k0 += 128u) {
         long long v[4];
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
             if (planes_b != planes_a) { *reinterpret_cast<std::uint32_t *>(planes_b + i8_boxed_offset(row, k0, p, S, I8<T>::NH, num_slabs)) = word; }
         }
     }
-    if (bad_rows != nullptr) {
+    if (bad_rows != nullptr && !pad_row) {
         #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             n_nonzero += __shfl_xor_sync(0xffffffffu, n_nonzero, o);
