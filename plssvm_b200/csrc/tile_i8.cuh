@@ -16,8 +16,9 @@
 // Tensor-core mapping (what makes it fast): the S accumulators of a 128 x 64 output block sit side by side in TMEM
 // (column t' * 64), and the B slices sit side by side in shared memory in q order, so ONE tcgen05.mma with N = 64 * m multiplies
 // slice A_p with the m consecutive slices B_q .. B_(q+m-1) and lands in the m consecutive accumulators t' .. t'+m-1:
-// 10 wide MMAs (N up to 256) per 32-feature step instead of 28 narrow ones, which cuts the shared-memory operand traffic
-// from 168 KB to 96 KB per step (107 B/clk at the tensor pipe's pace — under the 128 B/clk the SM can deliver).
+// 10 wide MMAs (N up to 256) per 32-feature step instead of 28 narrow ones, which cuts the shared-memory operand reads
+// from 168 KB to 96 KB per step (107 B/clk at the tensor pipe's pace; with the 42 KB the producer writes into the ring per step the
+// shared-memory port sees 154 B/clk against the 128 B/clk it delivers — that port, not L2 or the tensor pipe, bounds the kernel: DESIGN.md §3.0).
 //   * warp 0: producer — per 64-feature slab two contiguous bulk copies (cp.async.bulk) of pre-swizzled operand boxes: A = 128 rows x S planes
 //     (56 KB), B = 64 rows x S planes (28 KB); 2-stage ring (see split_i8_kernel for the layout in HBM)
 //   * warp 1: allocates all 512 TMEM columns (S x 64 int32 accumulator columns) and issues the MMAs from one elected lane
