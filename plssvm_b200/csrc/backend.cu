@@ -19,6 +19,7 @@
 #include "tile_tf32_2sm.cuh"
 #include "tile_tf32_n256.cuh"
 #include "tile_i8.cuh"
+#include "tile_i8_2sm.cuh"
 
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -182,6 +183,7 @@ struct plssvm_b200_ctx {
     int check_interval = 0;  // 0 = auto
     int verbose = 0;
     int ignore_convergence = 0;  // benchmarking: never set the convergence flag, so exactly the requested number of iterations runs
+    int max_ctas = 0;            // debugging: cap the grid of the tile kernels (0 = one CTA per SM)
     int linear_factorized = 0;  // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     // timings of the last call
     plssvm_b200_timings tm{};
@@ -210,6 +212,7 @@ struct plssvm_b200_dataset {
     void *X_i8 = nullptr, *X_i8b = nullptr, *rscale = nullptr;
     std::size_t ld8 = 0;
     int i8_slices = 0;    // number of digit planes X_i8 currently holds
+    int i8_br_b = 0;      // rows per box of the B-operand copy X_i8b
     int i8_bad_rows = 0;  // rows whose elements are spread over too many orders of magnitude for the automatic choice (split_i8_kernel)
 };
 
@@ -271,21 +274,25 @@ inline std::size_t rows_i8(const std::size_t rows) { return (rows + 127) / 128 *
 // number of int8 slices per operand for the tile-kernel choice `impl` (6: default, 7: exact-input count; the same for fp64)
 template <typename T>
 int i8_slices_for(const int impl) { return impl == 7 ? pb::I8<T>::S_EXACT : pb::I8<T>::S; }
-// int8-slice tile kernels: 6 default slice count, 7 exact-input slice count, 8 default slice count with 2 x 2 CTA clusters + TMA multicast
-inline bool is_i8(const int impl) { return impl == 6 || impl == 7 || impl == 8; }
+// int8-slice tile kernels: 6 default slice count, 7 exact-input slice count, 8 default slice count with 2 x 2 CTA clusters + TMA multicast,
+// 9 (fp32) CTA pairs with tcgen05.mma.cta_group::2 (tile_i8_2sm.cuh)
+inline bool is_i8(const int impl) { return impl >= 6 && impl <= 9; }
 // kernels whose tile range / ownership is over 256 x 256 super-tiles
-inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8; }
+inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8 || impl == 9; }
+// rows per box of the B-operand copy of the digit planes: what one CTA stages of a unit's columns
+template <typename T>
+int i8_br_b_for(const int impl) { return impl == 9 ? 64 : pb::I8<T>::NH; }
 
 // rows -> int8 digit planes + row scales (tile_i8.cuh); planes_a / planes_b (the same buffer for fp32) hold slices * rows_i8(rows) * ld8 bytes each
 template <typename T>
 void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes_a,
-                  std::int8_t *planes_b, const std::size_t ld8, T *rscale, int *bad_rows, cudaStream_t st) {
+                  std::int8_t *planes_b, const int br_b, const std::size_t ld8, T *rscale, int *bad_rows, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(rows_i8(rows) / 8);  // incl. the padding rows of the last box, which get zero digits
     const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), slabs = static_cast<std::uint32_t>(ld8 / 64);
     if (slices == pb::I8<T>::S) {
-        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, slabs, rscale, bad_rows);
+        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, static_cast<std::uint32_t>(br_b), slabs, rscale, bad_rows);
     } else {
-        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, slabs, rscale, bad_rows);
+        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, static_cast<std::uint32_t>(br_b), slabs, rscale, bad_rows);
     }
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
@@ -293,8 +300,8 @@ void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std:
 
 // digit planes of a resident data set, created on first use (re-created when another slice count is asked for)
 template <typename T>
-void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const int slices) {
-    if (ds->X_i8 != nullptr && ds->i8_slices == slices) { return; }
+void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const int slices, const int br_b) {
+    if (ds->X_i8 != nullptr && ds->i8_slices == slices && ds->i8_br_b == br_b) { return; }
     if (ds->X_i8 != nullptr) {
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ds->X_i8b != ds->X_i8) { PB_CUDA(cudaFree(ds->X_i8b)); }
@@ -306,13 +313,14 @@ void ensure_i8(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, const int slices) 
     const std::size_t plane_bytes = static_cast<std::size_t>(slices) * rows_i8(ds->N) * ds->ld8;
     PB_CUDA(cudaMalloc(&ds->X_i8, plane_bytes));
     ds->X_i8b = ds->X_i8;
-    if (pb::I8<T>::NH != TILE) { PB_CUDA(cudaMalloc(&ds->X_i8b, plane_bytes)); }
+    if (br_b != TILE) { PB_CUDA(cudaMalloc(&ds->X_i8b, plane_bytes)); }
+    ds->i8_br_b = br_b;
     PB_CUDA(cudaMalloc(&ds->rscale, (ds->N + 2) * sizeof(T)));
     ds->i8_slices = slices;
     int *bad_d = reinterpret_cast<int *>(static_cast<T *>(ds->rscale) + ds->N);  // scratch word behind the scales
     PB_CUDA(cudaMemsetAsync(bad_d, 0, sizeof(int), ctx->stream));
-    run_split_i8<T>(ctx, slices, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), static_cast<std::int8_t *>(ds->X_i8b), ds->ld8,
-                    static_cast<T *>(ds->rscale), bad_d, ctx->stream);
+    run_split_i8<T>(ctx, slices, static_cast<const T *>(ds->X), ds->N, ds->d, ds->ld, static_cast<std::int8_t *>(ds->X_i8), static_cast<std::int8_t *>(ds->X_i8b), br_b,
+                    ds->ld8, static_cast<T *>(ds->rscale), bad_d, ctx->stream);
     int *h = static_cast<int *>(ctx->pinned) + 512;  // second half of the pinned block (the first holds the CG state read-back)
     PB_CUDA(cudaMemcpyAsync(h, bad_d, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -338,7 +346,32 @@ template <typename T, int KERNEL, int MODE>
 void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
     const std::uint64_t ntiles = p.tile_hi - p.tile_lo;
     if (ntiles == 0) { return; }
-    const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms)));
+    const unsigned grid = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->max_ctas > 0 ? std::min(ctx->max_ctas, ctx->num_sms) : ctx->num_sms)));
+    if constexpr (sizeof(T) == 4) {
+        if (impl == 9) {  // int8-slice tiles on CTA pairs (tcgen05.mma.cta_group::2): the operand boxes are contiguous -> 2-D boxes of 128-byte lines
+            using L8 = pb::I8PairLayout<pb::I8<float>::S>;
+            PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
+            auto line_map = [&](CUtensorMap *tm, const std::int8_t *base, const std::size_t rows, const std::uint32_t box_lines) {
+                const cuuint64_t dims[2] = { 128, static_cast<cuuint64_t>(static_cast<std::size_t>(L8::S) * rows_i8(rows) * p.ld8 / 128) };
+                const cuuint64_t strides[1] = { 128 };
+                const cuuint32_t box[2] = { 128, box_lines };
+                const cuuint32_t estr[2] = { 1, 1 };
+                const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<std::int8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled (digit-plane lines) failed with code " + std::to_string(static_cast<int>(rc))); }
+            };
+            CUtensorMap tmA, tmB;
+            line_map(&tmA, p.A_i8, static_cast<std::size_t>(p.T_rows) * TILE, L8::A_BYTES / 128);
+            line_map(&tmB, p.B_i8, static_cast<std::size_t>(p.T_cols) * TILE, L8::BH_BYTES / 128);
+            const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(ctx->num_sms / 2)));
+            auto kern = pb::tile_kernel_i8_2sm<pb::I8<float>::S, KERNEL, MODE>;
+            PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
+            kern<<<2 * clusters, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmB, p);
+            PB_CUDA(cudaGetLastError());
+            ctx->tm.kernel_launches++;
+            return;
+        }
+    }
     if (is_i8(impl)) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 3 or 4, units of 128 x 128)
         PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
         auto launch = [&](auto slices, auto cluster) {
@@ -433,7 +466,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 template <typename T>
 int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
     // int8-slice tcgen05 tiles: beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA / 3xTF32 tiles
-    if (is_i8(ctx->impl)) { return features <= pb::I8_MAX_FEATURES ? ((sizeof(T) == 8 && ctx->impl == 7) ? 6 : ctx->impl) : 2; }
+    if (is_i8(ctx->impl)) { return features <= pb::I8_MAX_FEATURES ? ((sizeof(T) == 8 && (ctx->impl == 7 || ctx->impl == 9)) ? 6 : ctx->impl) : 2; }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
     // auto: int8 slices on tcgen05 (tile_i8.cuh) where the int32 accumulators cannot overflow; callers fall back to 2 for badly scaled
@@ -484,7 +517,7 @@ struct matvec_plan {
         const bool tiles_needed = !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR);
         impl = resolve_impl<T>(c, data->ld);
         if (is_i8(impl) && tiles_needed) {
-            ensure_i8<T>(c, const_cast<plssvm_b200_dataset *>(data), i8_slices_for<T>(impl));
+            ensure_i8<T>(c, const_cast<plssvm_b200_dataset *>(data), i8_slices_for<T>(impl), i8_br_b_for<T>(impl));
             if (!i8_allowed(c, data)) { impl = 2; }
         }
         if (sizeof(T) == 4 && tiles_needed && (impl == 2 || impl == 4 || impl == 5)) { ensure_tf32_split(c, const_cast<plssvm_b200_dataset *>(data)); }
@@ -920,8 +953,8 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
     T *stage_X[2] = { nullptr, nullptr }, *stage_sq[2] = { nullptr, nullptr }, *stage_hi[2] = { nullptr, nullptr }, *stage_lo[2] = { nullptr, nullptr };
     int impl = resolve_impl<T>(ctx, sv->ld);
     if (is_i8(impl) && kernel != pb::K_LINEAR) {  // int8 digit planes of both operands (tile_i8.cuh); host-staged points are split per batch below
-        ensure_i8<T>(ctx, sv, i8_slices_for<T>(impl));
-        if (pts_ds != nullptr) { ensure_i8<T>(ctx, const_cast<plssvm_b200_dataset *>(pts_ds), i8_slices_for<T>(impl)); }
+        ensure_i8<T>(ctx, sv, i8_slices_for<T>(impl), i8_br_b_for<T>(impl));
+        if (pts_ds != nullptr) { ensure_i8<T>(ctx, const_cast<plssvm_b200_dataset *>(pts_ds), i8_slices_for<T>(impl), i8_br_b_for<T>(impl)); }
         if (!i8_allowed(ctx, sv) || (pts_ds != nullptr && !i8_allowed(ctx, pts_ds))) { impl = 2; }
     }
     const bool need_i8 = kernel != pb::K_LINEAR && is_i8(impl);
@@ -995,7 +1028,7 @@ void predict_common(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alph
                     }
                 }
                 if (need_i8) {
-                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], stage_i8[buf], ld8, stage_sc[buf], nullptr, st);  // A operand only
+                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], stage_i8[buf], TILE, ld8, stage_sc[buf], nullptr, st);  // A operand only
                     P_i8 = stage_i8[buf];
                     P_scale = stage_sc[buf];
                 }
@@ -1166,9 +1199,10 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            PB_REQUIRE(value == 0 || value == 1 || value == 2 || (value >= 4 && value <= 8),
+            PB_REQUIRE(value == 0 || value == 1 || value == 2 || (value >= 4 && value <= 9),
                        "impl must be 0 (auto), 1 (simt), 2 (floating-point tensor tiles), 4 (fp32: CTA-pair 3xTF32), 5 (fp32: 128x256 3xTF32), 6 (int8-slice tcgen05 tiles) or "
-                       "7 (int8-slice tiles with the exact-input slice count: fp32 4 instead of 3 slices), 8 (int8-slice tiles, 2 x 2 CTA clusters with TMA multicast)");
+                       "7 (int8-slice tiles with the exact-input slice count: fp32 4 instead of 3 slices), 8 (int8-slice tiles, 2 x 2 CTA clusters with TMA multicast), "
+                       "9 (fp32: int8-slice tiles on CTA pairs, cta_group::2)");
             ctx->impl = static_cast<int>(value);
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");
@@ -1177,6 +1211,9 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
             ctx->verbose = value != 0;
         } else if (k == "ignore_convergence") {
             ctx->ignore_convergence = value != 0;
+        } else if (k == "max_ctas") {
+            PB_REQUIRE(value >= 0 && value <= 4096, "max_ctas out of range");
+            ctx->max_ctas = static_cast<int>(value);
         } else if (k == "linear_factorized") {
             ctx->linear_factorized = value != 0;
         } else {

@@ -83,7 +83,8 @@ struct I8Layout {
 // copies (cp.async.bulk, whole 128-byte lines) instead of 2-D / 3-D tensor boxes whose 64-byte rows halve TMA's request efficiency:
 //     box(R, ks) = all S planes of the BR rows [R BR, (R+1) BR) and the 64 features [64 ks, 64 ks + 64):  S x BR x 64 bytes, plane-major;
 //     offset(p, r, k) = (((r / BR) num_slabs + k / 64) S + p) BR 64 + (r % BR) 64 + ((((k % 64) / 16) ^ (((r % BR) / 2) % 4)) 16) + k % 16
-// The A operand (tile rows) uses BR = 128; the B operand (unit columns) BR = NH (fp64: 64 — a second copy; fp32: 128 — the same buffer).
+// The A operand (tile rows) uses BR = 128; the B operand (unit columns) BR = br_b = rows staged per CTA (fp64: 64 — a second copy; fp32: 128 — the
+// same buffer — or 64 for the CTA-pair kernel of tile_i8_2sm.cuh).
 // Rows are padded to a multiple of 128 and features to a multiple of 64 with zero digits (written by this kernel: launch it over the padded rows).
 // rscale[row] = 2^(e_row - 6); one warp per row.
 // The products are accurate to ~2^-(8S-2) sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
@@ -99,8 +100,8 @@ __host__ __device__ __forceinline__ std::size_t i8_boxed_offset(const std::size_
 
 template <typename T, int S>
 __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
-                                                       std::int8_t *__restrict__ planes_a, std::int8_t *__restrict__ planes_b, const std::uint32_t num_slabs,
-                                                       T *__restrict__ rscale, int *__restrict__ bad_rows) {
+                                                       std::int8_t *__restrict__ planes_a, std::int8_t *__restrict__ planes_b, const std::uint32_t br_b,
+                                                       const std::uint32_t num_slabs, T *__restrict__ rscale, int *__restrict__ bad_rows) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (rows + TILE - 1) / TILE * TILE) { return; }
     const bool pad_row = row >= rows;  // padding rows of the last 128-row box: all digits zero
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
                 v[j] = (v[j] - a) >> 8;  // exact
             }
             *reinterpret_cast<std::uint32_t *>(planes_a + i8_boxed_offset(row, k0, p, S, TILE, num_slabs)) = word;
-            if (planes_b != planes_a) { *reinterpret_cast<std::uint32_t *>(planes_b + i8_boxed_offset(row, k0, p, S, I8<T>::NH, num_slabs)) = word; }
+            if (planes_b != planes_a) { *reinterpret_cast<std::uint32_t *>(planes_b + i8_boxed_offset(row, k0, p, S, br_b, num_slabs)) = word; }
         }
     }
     if (bad_rows != nullptr && !pad_row) {
@@ -203,7 +204,7 @@ __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __h
 
 // CL = 1: one CTA per tile.  CL = 4: a cluster of 2 x 2 CTAs per 256 x 256 super-tile (launched with cluster dimension 4; the tile range is in
 // super-tiles like the CTA-pair 3xTF32 kernel's): CTA (r, c) computes tile (2 I2 + r, 2 J2 + c); the two CTAs of a cluster row need the same A
-// planes and the two of a cluster column the same B planes, so every CTA fetches only every other plane of its A block and of its B block and
+// planes and the two of a cluster column the same B planes, so every CTA fetches only one half of the planes of its A block and of its B block and
 // TMA multicasts it to its mate — half the L2 -> SM traffic per CTA (the single-CTA kernel runs at 92 % of the L2 throughput cap).  A stage is
 // refilled once the MMA warps of all three CTAs that write into or read from it have released it (multicast tcgen05.commit, count 3).
 template <typename T, int S_, int KERNEL, int MODE, int CL>
@@ -299,19 +300,12 @@ tile_kernel_i8(const TileParams<T> p) {
                             bulk_load(dst, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES, L8::A_BYTES, bar);
                             bulk_load(dst + L8::A_BYTES, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES, L8::B_BYTES, bar);
                         } else {
-                            // this CTA fetches every other plane of its row block / column block for itself and its mate
-                            #pragma unroll
-                            for (int pp = 0; pp < S; ++pp) {
-                                if ((pp & 1) == static_cast<int>(cc)) {
-                                    bulk_load_mc(dst + pp * L8::A_SLICE, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES + pp * L8::A_SLICE, L8::A_SLICE, bar, mask_a);
-                                }
-                            }
-                            #pragma unroll
-                            for (int pp = 0; pp < S; ++pp) {
-                                if ((pp & 1) == static_cast<int>(cr)) {
-                                    bulk_load_mc(dst + L8::A_BYTES + pp * L8::B_SLICE, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES + pp * L8::B_SLICE, L8::B_SLICE, bar, mask_b);
-                                }
-                            }
+                            // this CTA fetches one contiguous half of the planes of its row block / column block for itself and its mate
+                            constexpr int S0 = (S + 1) / 2;
+                            const int pa0 = cc == 0 ? 0 : S0, pa1 = cc == 0 ? S0 : S, pb0 = cr == 0 ? 0 : S0, pb1 = cr == 0 ? S0 : S;
+                            bulk_load_mc(dst + pa0 * L8::A_SLICE, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES + pa0 * L8::A_SLICE, static_cast<std::uint32_t>((pa1 - pa0) * L8::A_SLICE), bar, mask_a);
+                            bulk_load_mc(dst + L8::A_BYTES + pb0 * L8::B_SLICE, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES + pb0 * L8::B_SLICE,
+                                         static_cast<std::uint32_t>((pb1 - pb0) * L8::B_SLICE), bar, mask_b);
                         }
                         if (++stage == STAGES) {
                             stage = 0;

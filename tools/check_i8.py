@@ -101,34 +101,35 @@ for (N, d) in ((2, 3), (130, 1), (386, 65), (1000, 96), (2049, 333)):
         q, k_last = be.run_q_kernel(ds, kernel)
         v = np.random.default_rng(3).uniform(1, 2, n).astype(np.float32)
         outs = {}
-        for impl in (1, 2, 6, 8):
+        for impl in (1, 2, 6, 8, 9):
             be.set_option("impl", impl)
             outs[impl] = be.run_svm_kernel(ds, q, v, np.zeros_like(v), k_last + 1.0, 1.0, 1.0, kernel)
         be.set_option("impl", 0)
         want = orc.matvec(kid, X.astype(np.float64), q.astype(np.float64), v.astype(np.float64), np.zeros(n), float(k_last) + 1.0, 1.0, 1.0, gamma=1.0 / d)
         sc = np.max(np.abs(want))
         e = {i: np.max(np.abs(outs[i] - want)) / sc for i in outs}
-        worst32 = max(worst32, e[6], e[8])
-        print(f"fp32 N={N:5d} d={d:4d} {kernel:10s} simt {e[1]:.2e}  tf32x3 {e[2]:.2e}  i8 {e[6]:.2e}  i8-cluster {e[8]:.2e}  (vs fp64 oracle)", flush=True)
+        worst32 = max(worst32, e[6], e[8], e[9])
+        print(f"fp32 N={N:5d} d={d:4d} {kernel:10s} simt {e[1]:.2e}  tf32x3 {e[2]:.2e}  i8 {e[6]:.2e}  i8-cluster {e[8]:.2e}  i8-pair {e[9]:.2e} identical {np.array_equal(outs[6], outs[9])}  (vs fp64 oracle)", flush=True)
 print("worst fp32 i8 matvec error:", worst32, "OK" if worst32 < 2e-6 else "FAIL", flush=True)
 X, y = make_data(3000, 200, 11, np.float32)
 P, _ = make_data(700, 200, 10, np.float32)
 alpha = np.random.default_rng(5).standard_normal(3000).astype(np.float32)
 for kernel in ("polynomial", "rbf"):
     vals = {}
-    for impl in (2, 6):
+    for impl in (2, 6, 9):
         be.set_option("impl", impl)
         vals[impl], _ = be.predict_values(be.dataset(X), alpha, 0.1, be.dataset(P), kernel)
         vals[(impl, "host")], _ = be.predict_values(X, alpha, 0.1, P, kernel)
     sc = np.max(np.abs(vals[2]))
-    print(f"fp32 predict {kernel}: |i8 - tf32x3| / scale = {np.max(np.abs(vals[6] - vals[2])) / sc:.2e}   host-staged: {np.max(np.abs(vals[(6, 'host')] - vals[2])) / sc:.2e}", flush=True)
+    print(f"fp32 predict {kernel}: |i8 - tf32x3| / scale = {np.max(np.abs(vals[6] - vals[2])) / sc:.2e}   host-staged: {np.max(np.abs(vals[(6, 'host')] - vals[2])) / sc:.2e}"
+          f"   pair identical: {np.array_equal(vals[6], vals[9])} / {np.array_equal(vals[(6, 'host')], vals[(9, 'host')])}", flush=True)
 be.set_option("impl", 0)
 for (N, d, kernel) in ((32769, 1024, "polynomial"), (32769, 4096, "rbf")):
     X, y = make_data(N, d, 9, np.float32)
     ds = be.dataset(X)
     q, k_last = be.run_q_kernel(ds, kernel)
     v = np.ones(N - 1, np.float32)
-    for impl in (2, 6, 8):
+    for impl in (2, 6, 8, 9):
         be.set_option("impl", impl)
         ts = []
         for _ in range(4):

@@ -12,7 +12,7 @@ import plssvm_b200 as pb  # noqa: E402
 from datagen import make_data  # noqa: E402
 
 be = pb.Backend(0)
-impls = {np.float64: (1, 2, 6), np.float32: (1, 2, 4, 5, 6, 7)}
+impls = {np.float64: (1, 2, 6, 8), np.float32: (1, 2, 4, 5, 6, 7, 8, 9)}
 for dtype in (np.float64, np.float32):
     X, y = make_data(301, 37, 1, dtype)
     P, _ = make_data(150, 37, 2, dtype)
