@@ -66,7 +66,9 @@ const char *plssvm_b200_last_error(void);
  * the floating-point tensor tiles for more than 16384 features or badly scaled rows), 1 SIMT FMA tiles, 2 floating-point tensor
  * tiles (fp64: TMA + DMMA, fp32: tcgen05 3xTF32), 4 / 5 fp32 3xTF32 variants (CTA pair / 128x256), 6 int8 slices on tcgen05
  * kind::i8 with exact int32 accumulation (fp64: 7 slices = 54 bits, fp32: 3 slices = 22 bits), 7 the same with 4 slices
- * (30 bits) for fp32; "check_interval" (CG iterations between host polls),
+ * (30 bits) for fp32, 8 / 9 measured-but-not-faster variants of 6 kept for reference (2 x 2 CTA clusters with TMA multicast /
+ * fp32 CTA pairs with cta_group::2; bit-identical results); "max_ctas" (debugging: cap the number of persistent CTAs of the
+ * tile kernels, 0 = one per SM); "check_interval" (CG iterations between host polls),
  * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571), "linear_factorized" (0/1: for the linear kernel
  * evaluate Q~ v as X (X^T v) + rank-2 terms — two streaming passes over X, O(n d) instead of O(n^2 d); default 0 = the
  * implicit tiled formulation the reference uses), "ignore_convergence" (0/1, benchmarking only: the stopping test is
