@@ -89,6 +89,9 @@ uint64_t plssvm_b200_tri_num_tiles(uint64_t tiles_per_side);
 uint64_t plssvm_b200_tri_encode(uint64_t tiles_per_side, uint64_t I, uint64_t J);
 void plssvm_b200_tri_decode(uint64_t tiles_per_side, uint64_t L, uint32_t *I, uint32_t *J);
 void plssvm_b200_rank_range(uint64_t total, int rank, int world_size, uint64_t *lo, uint64_t *hi);
+/* byte offset of digit `plane` of element (row, feature) in the boxed, pre-swizzled layout of the int8 digit planes: boxes of
+ * `box_rows` rows x 64 features x `planes` planes, each box the SWIZZLE_64B shared-memory image tcgen05.mma reads */
+uint64_t plssvm_b200_i8_plane_offset(uint64_t row, uint32_t feature, uint32_t plane, uint32_t planes, uint32_t box_rows, uint32_t slabs);
 
 /* ---- datasets ----------------------------------------------------------------------------------------------------
  * Upload (or adopt from device memory when src_on_device != 0) a dense row-major N x d matrix.  The library keeps its

@@ -87,6 +87,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.plssvm_b200_tri_decode.restype = None
     lib.plssvm_b200_tri_decode.argtypes = [u64, u64, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
     lib.plssvm_b200_rank_range.restype = None
+    lib.plssvm_b200_i8_plane_offset.restype = u64
+    lib.plssvm_b200_i8_plane_offset.argtypes = [u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
     lib.plssvm_b200_rank_range.argtypes = [u64, i32, i32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     lib.plssvm_b200_dataset_destroy.argtypes = [vp]
     lib.plssvm_b200_cg_step.argtypes = [vp, u64, ctypes.POINTER(u64), ctypes.POINTER(i32)]
@@ -112,7 +114,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
 EXPORTED_SYMBOLS = [
     "plssvm_b200_create", "plssvm_b200_destroy", "plssvm_b200_last_error", "plssvm_b200_set_option", "plssvm_b200_get_timings", "plssvm_b200_device_count",
     "plssvm_b200_comm_unique_id", "plssvm_b200_comm_init", "plssvm_b200_tile_size", "plssvm_b200_tri_num_tiles", "plssvm_b200_tri_encode", "plssvm_b200_tri_decode",
-    "plssvm_b200_rank_range", "plssvm_b200_dataset_destroy", "plssvm_b200_cg_step", "plssvm_b200_cg_abort",
+    "plssvm_b200_rank_range", "plssvm_b200_i8_plane_offset", "plssvm_b200_dataset_destroy", "plssvm_b200_cg_step", "plssvm_b200_cg_abort",
 ] + [f"plssvm_b200_{name}_{suf}" for suf in ("f32", "f64")
      for name in ("dataset_create", "solve", "solve_dataset", "cg_begin", "cg_finish", "cg_trace", "predict", "predict_dataset", "q_kernel", "matvec", "w_kernel", "predict_kernel")]
 
@@ -145,6 +147,11 @@ def rank_range(total: int, rank: int, world_size: int):
     lo, hi = ctypes.c_uint64(), ctypes.c_uint64()
     load_library().plssvm_b200_rank_range(total, rank, world_size, ctypes.byref(lo), ctypes.byref(hi))
     return int(lo.value), int(hi.value)
+
+
+def i8_plane_offset(row: int, feature: int, plane: int, planes: int, box_rows: int, slabs: int) -> int:
+    """Byte offset of one digit in the boxed, pre-swizzled plane layout of the int8-slice tile kernel."""
+    return int(load_library().plssvm_b200_i8_plane_offset(row, feature, plane, planes, box_rows, slabs))
 
 
 def broadcast_bytes(raw: bytes, size: int, src: int = 0, device: int = 0) -> bytes:

@@ -1264,6 +1264,9 @@ uint64_t plssvm_b200_tri_num_tiles(uint64_t tiles_per_side) { return pb::tri_num
 uint64_t plssvm_b200_tri_encode(uint64_t tiles_per_side, uint64_t I, uint64_t J) { return pb::tri_encode(tiles_per_side, I, J); }
 void plssvm_b200_tri_decode(uint64_t tiles_per_side, uint64_t L, uint32_t *I, uint32_t *J) { pb::tri_decode(tiles_per_side, L, *I, *J); }
 void plssvm_b200_rank_range(uint64_t total, int rank, int world_size, uint64_t *lo, uint64_t *hi) { pb::rank_range(total, rank, world_size, *lo, *hi); }
+uint64_t plssvm_b200_i8_plane_offset(uint64_t row, uint32_t feature, uint32_t plane, uint32_t planes, uint32_t box_rows, uint32_t slabs) {
+    return static_cast<uint64_t>(pb::i8_boxed_offset(static_cast<std::size_t>(row), feature, plane, planes, box_rows, slabs));
+}
 
 int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
     return guarded([&] {

@@ -88,6 +88,29 @@ def test_rank_ranges_partition_the_triangle_evenly(world):
     assert max(sizes) - min(sizes) <= 1
 
 
+@pytest.mark.parametrize("planes,box_rows", [(7, 128), (7, 64), (3, 128), (3, 64)])
+def test_int8_plane_layout_is_a_bijection_of_swizzled_boxes(planes, box_rows):
+    """The digit planes are stored as contiguous operand boxes that already are the shared-memory image tcgen05.mma expects:
+    box (R, ks) = planes x box_rows x 64 bytes, plane-major; inside a plane K-major rows of 64 bytes whose 16-byte chunks are XOR-swizzled
+    with bits 1..2 of the row (SWIZZLE_64B).  Host-only: the offset function is the single source of truth of kernel and split."""
+    slabs, rows = 3, 2 * box_rows
+    seen = set()
+    for r in range(rows):
+        for k in range(0, 64 * slabs, 4):  # the split kernel writes 4 consecutive features per store
+            for p in range(planes):
+                off = pb.i8_plane_offset(r, k, p, planes, box_rows, slabs)
+                assert off % 4 == 0 and off not in seen
+                seen.add(off)
+                box, within = divmod(off, planes * box_rows * 64)
+                assert box == (r // box_rows) * slabs + k // 64
+                plane, in_plane = divmod(within, box_rows * 64)
+                assert plane == p
+                rr, byte = divmod(in_plane, 64)
+                assert rr == r % box_rows
+                assert byte == ((((k % 64) // 16) ^ ((rr // 2) % 4)) * 16 + k % 16)
+    assert len(seen) == rows * 16 * slabs * planes and max(seen) < planes * rows * 64 * slabs
+
+
 def test_tile_size_matches_design():
     assert pb.tile_size() == 128
 
