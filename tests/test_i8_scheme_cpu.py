@@ -26,14 +26,14 @@ def split(x, S):
     return np.stack(planes), e, value
 
 
-def sliced_dot(A, B, S):
+def sliced_dot(A, B, S, drop=()):
     pa, ea, _ = split(A, S)
     pb_, eb, _ = split(B, S)
     acc = [np.zeros((A.shape[0], B.shape[0]), dtype=np.int64) for _ in range(S)]
     for p in range(S):
         for q in range(S):
             t = p + q - (S - 1)
-            if t >= 0:  # the S most significant digit diagonals only
+            if t >= 0 and (p, q) not in drop:  # the S most significant digit diagonals only
                 acc[t] += pa[p] @ pb_[q].T
     s = acc[0].astype(np.float64)
     for t in range(1, S):
@@ -74,6 +74,17 @@ def test_seven_slices_are_at_least_as_accurate_as_fp64(d):
     assert err_i8 <= max(err_f64, 2.0 ** -56)
     assert err_i8 < 2.0 ** -53
     assert max(int(np.abs(a).max()) for a in acc) < 2 ** 31
+
+
+def test_all_28_products_are_needed_for_fp64_accuracy():
+    """The product count of the fp64 kernel is minimal: leaving out even the two least significant products (lowest plane x highest plane)
+    puts the result above the error of a native fp64 dot product."""
+    A, B = data(4096, 2)
+    exact = A.astype(np.longdouble) @ B.astype(np.longdouble).T
+    scale = np.sqrt((A * A).sum(1))[:, None] * np.sqrt((B * B).sum(1))[None, :]
+    err_f64 = float(np.max(np.abs(A @ B.T - exact) / scale))
+    err_26 = float(np.max(np.abs(sliced_dot(A, B, 7, drop=((0, 6), (6, 0)))[0] - exact) / scale))
+    assert err_26 > 4.0 * err_f64
 
 
 def test_fp32_slice_counts():
