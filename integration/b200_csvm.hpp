@@ -11,7 +11,10 @@
 #ifndef PLSSVM_B200_INTEGRATION_CSVM_HPP_
 #define PLSSVM_B200_INTEGRATION_CSVM_HPP_
 
+#include "plssvm/backend_types.hpp"          // plssvm::backend_type
 #include "plssvm/csvm.hpp"                  // plssvm::csvm
+#include "plssvm/detail/logger.hpp"         // plssvm::detail::log, plssvm::verbosity_level
+#include "plssvm/detail/performance_tracker.hpp"  // plssvm::detail::tracking_entry, PLSSVM_DETAIL_PERFORMANCE_TRACKER_ADD_TRACKING_ENTRY
 #include "plssvm/detail/type_traits.hpp"    // PLSSVM_REQUIRES
 #include "plssvm/exceptions/exceptions.hpp" // plssvm::exception
 #include "plssvm/parameter.hpp"             // plssvm::parameter, plssvm::detail::parameter, has_only_parameter_named_args_v
@@ -19,8 +22,13 @@
 
 #include "plssvm_b200/csvm.hpp"  // plssvm::b200::csvm (C-ABI adaptor)
 
+#include "fmt/chrono.h"
 #include "fmt/core.h"
 
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <numeric>
 #include <string>
 #include <utility>
 #include <vector>
@@ -56,16 +64,34 @@ class csvm : public ::plssvm::csvm {
     [[nodiscard]] std::vector<double> predict_values(const ::plssvm::detail::parameter<double> &params, const std::vector<std::vector<double>> &support_vectors, const std::vector<double> &alpha, double rho, std::vector<double> &w, const std::vector<std::vector<double>> &predict_points) const final { return this->predict_impl(params, support_vectors, alpha, rho, w, predict_points); }
 
   private:
+    // cuda::csvm::init (src/plssvm/backends/CUDA/csvm.cu:48-86): target check, every visible device, the same log lines and tracker entries.
+    // PLSSVM_B200_NUM_DEVICES=k restricts the backend to the first k visible devices (CUDA_VISIBLE_DEVICES selects which).
     void init(const target_platform target) {
         if (target != target_platform::automatic && target != target_platform::gpu_nvidia) {
             throw backend_exception{ fmt::format("Invalid target platform '{}' for the B200 backend!", target) };
         }
+        ::plssvm::detail::log(verbosity_level::full, "\nUsing B200 as backend.\n");
+#if defined(PLSSVM_HAS_B200_BACKEND)
+        PLSSVM_DETAIL_PERFORMANCE_TRACKER_ADD_TRACKING_ENTRY((::plssvm::detail::tracking_entry{ "backend", "backend", ::plssvm::backend_type::b200 }));
+#endif
+        PLSSVM_DETAIL_PERFORMANCE_TRACKER_ADD_TRACKING_ENTRY((::plssvm::detail::tracking_entry{ "backend", "target_platform", ::plssvm::target_platform::gpu_nvidia }));
+        int count = 0;
+        if (plssvm_b200_device_count(&count) != PLSSVM_B200_OK || count == 0) {
+            throw backend_exception{ "B200 backend selected but no CUDA capable devices were found!" };
+        }
+        if (const char *env = std::getenv("PLSSVM_B200_NUM_DEVICES"); env != nullptr && std::atoi(env) > 0) {
+            count = std::min(count, std::atoi(env));
+        }
+        std::vector<int> devices(static_cast<std::size_t>(count));
+        std::iota(devices.begin(), devices.end(), 0);
         try {
-            impl_ = ::plssvm::b200::csvm{ 0 };
+            impl_ = ::plssvm::b200::csvm{ devices };
         } catch (const ::plssvm::b200::backend_exception &e) {
             throw backend_exception{ e.what() };
         }
         target_ = plssvm::target_platform::gpu_nvidia;
+        ::plssvm::detail::log(verbosity_level::full, "Found {} B200 device(s).\n", ::plssvm::detail::tracking_entry{ "backend", "num_devices", devices.size() });
+        ::plssvm::detail::log(verbosity_level::full | verbosity_level::timing, "\n");
     }
 
     template <typename T>
@@ -78,10 +104,34 @@ class csvm : public ::plssvm::csvm {
         out.cost = p.cost.value();
         return out;
     }
+    // The CG loop runs on the device without a host round trip per iteration, so the per-iteration lines of the reference's loop
+    // (gpu_csvm.hpp:569-571, 559-563) are emitted after the solve from the residual history the device recorded; the summary line carries
+    // the same tracking entries (gpu_csvm.hpp:637-646).
     template <typename T>
     [[nodiscard]] std::pair<std::vector<T>, T> solve_impl(const ::plssvm::detail::parameter<T> &params, const std::vector<std::vector<T>> &A, std::vector<T> b, const T eps, const unsigned long long max_iter) const {
         try {
-            return impl_.solve_system_of_linear_equations(convert(params), A, std::move(b), eps, max_iter);
+            auto result = impl_.solve_system_of_linear_equations(convert(params), A, std::move(b), eps, max_iter);
+            const plssvm_b200_timings st = impl_.last_stats();
+            const T delta = static_cast<T>(st.cg_residuum), target = static_cast<T>(st.cg_target_residuum);
+            const auto avg_time = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::duration<double, std::milli>(st.cg_avg_iteration_ms));
+            if (::plssvm::verbosity != verbosity_level::quiet && ((verbosity_level::full | verbosity_level::timing) & ::plssvm::verbosity) != verbosity_level::quiet) {
+                const std::vector<double> trace = impl_.last_trace();
+                for (std::size_t k = 0; k + 1 < trace.size(); ++k) {
+                    ::plssvm::detail::log(verbosity_level::full | verbosity_level::timing, "Start Iteration {} (max: {}) with current residuum {} (target: {}). ", k + 1, max_iter,
+                                          static_cast<T>(trace[k]), target);
+                    ::plssvm::detail::log(verbosity_level::full | verbosity_level::timing, "Done in {}.\n", avg_time);
+                }
+            }
+            ::plssvm::detail::log(verbosity_level::full | verbosity_level::timing,
+                                  "Finished after {}/{} iterations with a residuum of {} (target: {}) and an average iteration time of {}.\n",
+                                  ::plssvm::detail::tracking_entry{ "cg", "iterations", static_cast<unsigned long long>(st.cg_iterations) },
+                                  ::plssvm::detail::tracking_entry{ "cg", "max_iterations", max_iter },
+                                  ::plssvm::detail::tracking_entry{ "cg", "residuum", delta },
+                                  ::plssvm::detail::tracking_entry{ "cg", "target_residuum", target },
+                                  ::plssvm::detail::tracking_entry{ "cg", "avg_iteration_time", avg_time });
+            PLSSVM_DETAIL_PERFORMANCE_TRACKER_ADD_TRACKING_ENTRY((::plssvm::detail::tracking_entry{ "cg", "epsilon", eps }));
+            ::plssvm::detail::log(verbosity_level::libsvm, "optimization finished, #iter = {}\n", static_cast<unsigned long long>(st.cg_iterations));
+            return result;
         } catch (const ::plssvm::b200::backend_exception &e) {
             throw backend_exception{ e.what() };
         }

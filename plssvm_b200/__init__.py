@@ -47,10 +47,12 @@ class BackendError(RuntimeError):
 class Timings(ctypes.Structure):
     _fields_ = [("total_ms", ctypes.c_double), ("cg_loop_ms", ctypes.c_double), ("matvec_ms", ctypes.c_double), ("matvec_tile_ms", ctypes.c_double),
                 ("matvec_calls", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("matvec_flops", ctypes.c_double), ("h2d_bytes", ctypes.c_double),
-                ("d2h_bytes", ctypes.c_double), ("impl_used", ctypes.c_int), ("reserved", ctypes.c_int)]
+                ("d2h_bytes", ctypes.c_double), ("impl_used", ctypes.c_int), ("n_devices", ctypes.c_int),
+                ("cg_iterations", ctypes.c_uint64), ("cg_max_iterations", ctypes.c_uint64), ("cg_residuum", ctypes.c_double), ("cg_target_residuum", ctypes.c_double),
+                ("cg_epsilon", ctypes.c_double), ("cg_avg_iteration_ms", ctypes.c_double), ("rebalances", ctypes.c_uint64), ("fallback_batches", ctypes.c_uint64)]
 
     def as_dict(self) -> dict:
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _LIB: Optional[ctypes.CDLL] = None
@@ -72,7 +74,11 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib = ctypes.CDLL(_build.LIB)
     vp, sz, i32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
     lib.plssvm_b200_last_error.restype = ctypes.c_char_p
-    lib.plssvm_b200_create.argtypes = [i32, ctypes.POINTER(vp)]
+    lib.plssvm_b200_create.argtypes = [ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+    lib.plssvm_b200_num_devices.argtypes = [vp, ctypes.POINTER(i32)]
+    lib.plssvm_b200_last_trace.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
+    lib.plssvm_b200_weighted_range.restype = None
+    lib.plssvm_b200_weighted_range.argtypes = [u64, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64), ctypes.POINTER(u64)]
     lib.plssvm_b200_destroy.argtypes = [vp]
     lib.plssvm_b200_set_option.argtypes = [vp, ctypes.c_char_p, ctypes.c_longlong]
     lib.plssvm_b200_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
@@ -95,7 +101,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.plssvm_b200_cg_abort.argtypes = [vp]
     for suf, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
         getattr(lib, f"plssvm_b200_dataset_create_{suf}").argtypes = [vp, vp, sz, sz, i32, ctypes.POINTER(vp)]
+        getattr(lib, f"plssvm_b200_dataset_create_rows_{suf}").argtypes = [vp, vp, sz, sz, ctypes.POINTER(vp)]
         getattr(lib, f"plssvm_b200_solve_{suf}").argtypes = [vp, vp, sz, sz, vp, i32, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
+        getattr(lib, f"plssvm_b200_solve_rows_{suf}").argtypes = [vp, vp, sz, sz, vp, i32, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
+        getattr(lib, f"plssvm_b200_predict_rows_{suf}").argtypes = [vp, vp, sz, sz, vp, ct, vp, vp, vp, sz, i32, i32, ct, ct, vp]
         getattr(lib, f"plssvm_b200_solve_dataset_{suf}").argtypes = [vp, vp, vp, i32, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
         getattr(lib, f"plssvm_b200_cg_begin_{suf}").argtypes = [vp, vp, vp, i32, i32, ct, ct, ct, ct, ctypes.POINTER(vp)]
         getattr(lib, f"plssvm_b200_cg_finish_{suf}").argtypes = [vp, vp, vp, vp, vp]
@@ -112,11 +121,13 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
 
 # every symbol include/plssvm_b200.h declares (tests/test_boundary.py checks the header against this list and the .so)
 EXPORTED_SYMBOLS = [
-    "plssvm_b200_create", "plssvm_b200_destroy", "plssvm_b200_last_error", "plssvm_b200_set_option", "plssvm_b200_get_timings", "plssvm_b200_device_count",
-    "plssvm_b200_comm_unique_id", "plssvm_b200_comm_init", "plssvm_b200_tile_size", "plssvm_b200_tri_num_tiles", "plssvm_b200_tri_encode", "plssvm_b200_tri_decode",
-    "plssvm_b200_rank_range", "plssvm_b200_i8_plane_offset", "plssvm_b200_dataset_destroy", "plssvm_b200_cg_step", "plssvm_b200_cg_abort",
+    "plssvm_b200_create", "plssvm_b200_destroy", "plssvm_b200_num_devices", "plssvm_b200_last_error", "plssvm_b200_set_option", "plssvm_b200_get_timings", "plssvm_b200_device_count",
+    "plssvm_b200_has_experimental", "plssvm_b200_last_trace", "plssvm_b200_comm_unique_id", "plssvm_b200_comm_init", "plssvm_b200_tile_size", "plssvm_b200_tri_num_tiles", "plssvm_b200_tri_encode",
+    "plssvm_b200_tri_decode", "plssvm_b200_rank_range", "plssvm_b200_weighted_range", "plssvm_b200_i8_plane_offset", "plssvm_b200_dataset_destroy", "plssvm_b200_cg_step",
+    "plssvm_b200_cg_abort",
 ] + [f"plssvm_b200_{name}_{suf}" for suf in ("f32", "f64")
-     for name in ("dataset_create", "solve", "solve_dataset", "cg_begin", "cg_finish", "cg_trace", "predict", "predict_dataset", "q_kernel", "matvec", "w_kernel", "predict_kernel")]
+     for name in ("dataset_create", "dataset_create_rows", "solve", "solve_rows", "solve_dataset", "cg_begin", "cg_finish", "cg_trace", "predict", "predict_rows", "predict_dataset",
+                  "q_kernel", "matvec", "w_kernel", "predict_kernel")]
 
 
 def _check(rc: int) -> None:
@@ -147,6 +158,25 @@ def rank_range(total: int, rank: int, world_size: int):
     lo, hi = ctypes.c_uint64(), ctypes.c_uint64()
     load_library().plssvm_b200_rank_range(total, rank, world_size, ctypes.byref(lo), ctypes.byref(hi))
     return int(lo.value), int(hi.value)
+
+
+def weighted_range(total: int, rank: int, world_size: int, weights):
+    """Rate-weighted contiguous share of `total` tiles (option "balance"); the ranges of all ranks tile [0, total) exactly."""
+    lo, hi = ctypes.c_uint64(), ctypes.c_uint64()
+    w = (ctypes.c_double * world_size)(*[float(x) for x in weights])
+    load_library().plssvm_b200_weighted_range(total, rank, world_size, w, ctypes.byref(lo), ctypes.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
+def has_experimental() -> bool:
+    """True if the library was built with -DPLSSVM_B200_EXPERIMENTAL (tile-kernel variants 4 / 5 / 8 / 9)."""
+    return bool(load_library().plssvm_b200_has_experimental())
+
+
+def _row_pointers(X: np.ndarray):
+    """Array of row pointers into a C-contiguous 2-D array (the std::vector<std::vector<T>> view of the *_rows entry points)."""
+    base, stride = X.ctypes.data, X.strides[0]
+    return (ctypes.c_void_p * X.shape[0])(*[base + i * stride for i in range(X.shape[0])])
 
 
 def i8_plane_offset(row: int, feature: int, plane: int, planes: int, box_rows: int, slabs: int) -> int:
@@ -236,13 +266,26 @@ class Dataset:
 
 
 class Backend:
-    """One context per GPU / rank (~ ``cuda::csvm::init``, CUDA/csvm.cu:48-86).  Raises :class:`BackendError` without a B200."""
+    """One context for the GPUs this process drives (~ ``cuda::csvm::init``, CUDA/csvm.cu:48-86).  ``Backend(i)``: device i;
+    ``Backend(devices=[...])``: a device group — data sets replicated, matvec tiles and predict points sharded over the devices;
+    ``Backend(devices="all")``: every visible device like the reference's backends.  Raises :class:`BackendError` without a B200."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, *, devices=None):
         self.lib = load_library()
         self._h = ctypes.c_void_p()
-        _check(self.lib.plssvm_b200_create(device, ctypes.byref(self._h)))
-        self.device = device
+        if devices is None:
+            devices = [int(device)]
+        if isinstance(devices, str):
+            if devices != "all":
+                raise ValueError("devices must be a list of device indices or 'all'")
+            _check(self.lib.plssvm_b200_create(None, 0, ctypes.byref(self._h)))
+        else:
+            ids = (ctypes.c_int * len(devices))(*[int(x) for x in devices])
+            _check(self.lib.plssvm_b200_create(ids, len(devices), ctypes.byref(self._h)))
+        n = ctypes.c_int()
+        _check(self.lib.plssvm_b200_num_devices(self._h, ctypes.byref(n)))
+        self.num_devices = int(n.value)
+        self.device = int(device) if isinstance(devices, str) else int(devices[0])
         self.rank, self.world_size = 0, 1
 
     def close(self) -> None:
@@ -263,6 +306,13 @@ class Backend:
         t = Timings()
         _check(self.lib.plssvm_b200_get_timings(self._h, ctypes.byref(t)))
         return t.as_dict()
+
+    def last_trace(self) -> np.ndarray:
+        """Residual history r.r of the last finished solve (entry k: after k iterations)."""
+        out = np.empty(4097, dtype=np.float64)
+        count = ctypes.c_size_t()
+        _check(self.lib.plssvm_b200_last_trace(self._h, _ptr(out), out.size, ctypes.byref(count)))
+        return out[: count.value].copy()
 
     # -- multi-GPU ------------------------------------------------------------------------------------------------------------
     def init_comm_from_torch(self) -> None:
@@ -312,6 +362,36 @@ class Backend:
             fn = getattr(self.lib, f"plssvm_b200_solve_{suf}")
             _check(fn(self._h, _ptr(X), N, d, _ptr(yh), k, int(degree), gamma, coef0, cost, eps, max_iter, _ptr(alpha), _ptr(rho), _ptr(iters), _ptr(res)))
         return {"alpha": alpha, "rho": rho[0], "iterations": int(iters[0]), "delta": res[0], "delta0": res[1]}
+
+    def solve_rows(self, X, y, kernel, *, degree=3, gamma=None, coef0=0.0, cost=1.0, eps=1e-3, max_iter=None):
+        """``solve`` through plssvm_b200_solve_rows_*: the matrix is handed over as row pointers (the reference's vector<vector<T>>)."""
+        X = _host(X)
+        N, d = X.shape
+        suf = _suffix(X.dtype)
+        yh = _host(y, X.dtype)
+        gamma = 1.0 / d if gamma is None else gamma
+        max_iter = N if max_iter is None else int(max_iter)
+        alpha, rho, iters, res = np.empty(N, dtype=X.dtype), np.zeros(1, dtype=X.dtype), np.zeros(1, dtype=np.uint64), np.zeros(2, dtype=X.dtype)
+        rows = _row_pointers(X)
+        _check(getattr(self.lib, f"plssvm_b200_solve_rows_{suf}")(self._h, ctypes.cast(rows, ctypes.c_void_p), N, d, _ptr(yh), kernel_id(kernel), int(degree), gamma, coef0, cost, eps,
+                                                                  max_iter, _ptr(alpha), _ptr(rho), _ptr(iters), _ptr(res)))
+        return {"alpha": alpha, "rho": rho[0], "iterations": int(iters[0]), "delta": res[0], "delta0": res[1]}
+
+    def predict_values_rows(self, SV, alpha, rho, points, kernel, *, degree=3, gamma=None, coef0=0.0):
+        """``predict_values`` through plssvm_b200_predict_rows_* (support vectors and points as row pointers)."""
+        SV = _host(SV)
+        points = _host(points, SV.dtype)
+        n_sv, d = SV.shape
+        suf = _suffix(SV.dtype)
+        alpha = _host(alpha, SV.dtype)
+        gamma = 1.0 / d if gamma is None else gamma
+        out = np.empty(points.shape[0], dtype=SV.dtype)
+        w_buf, w_valid = np.zeros(d, dtype=SV.dtype), ctypes.c_int(0)
+        sv_rows, pt_rows = _row_pointers(SV), _row_pointers(points)
+        _check(getattr(self.lib, f"plssvm_b200_predict_rows_{suf}")(self._h, ctypes.cast(sv_rows, ctypes.c_void_p), n_sv, d, _ptr(alpha), rho, _ptr(w_buf),
+                                                                    ctypes.cast(ctypes.byref(w_valid), ctypes.c_void_p), ctypes.cast(pt_rows, ctypes.c_void_p), points.shape[0],
+                                                                    kernel_id(kernel), int(degree), gamma, coef0, _ptr(out)))
+        return out, (w_buf if w_valid.value else None)
 
     def solve_traced(self, X, y, kernel, *, degree=3, gamma=None, coef0=0.0, cost=1.0, eps=1e-3, max_iter=None, interval=8):
         """``solve`` through the session API, additionally returning the residual history under ``"trace"``."""

@@ -32,9 +32,10 @@ struct TileParams {
     const T *B;
     const T *A_hi, *A_lo;  // fp32 tensor path only: TF32 hi / lo split of A and B (tile_tf32.cuh)
     const T *B_hi, *B_lo;
-    // int8-slice tensor path only (tile_i8.cuh): digit planes of A (boxes of 128 rows) and B (boxes of NH rows) in the boxed, pre-swizzled
-    // layout of split_i8_kernel, and the per-row scales 2^(e - 6)
-    const std::int8_t *A_i8, *B_i8;
+    // int8-slice tensor path only (tile_i8.cuh): digit planes of A and B in the boxed, pre-swizzled layout of split_i8_kernel (boxes of 128
+    // rows; the B operand of a 128 x NH unit is a row range of such a box), and the per-row scales 2^(e - 6).  B_i8b: a second copy of B's
+    // planes in boxes of 64 rows, read only by the experimental CTA-pair kernel (tile_i8_2sm.cuh)
+    const std::int8_t *A_i8, *B_i8, *B_i8b;
     const T *A_scale, *B_scale;
     std::uint32_t ld8;               // features padded to a multiple of 64 (= 64 x number of slabs)
     std::uint32_t n_rows;  // valid rows of A  (SYM: n = N - 1)

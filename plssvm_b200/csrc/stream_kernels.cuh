@@ -22,19 +22,38 @@ __global__ void pack_rows_kernel(const T *__restrict__ src, T *__restrict__ dst,
 
 // ---- row statistics: one warp per row ------------------------------------------------------------------------------------
 // sq[i] = |x_i|^2  (rbf epilogue of the tile kernels)
+// `mean` (optional, ld entries, pad columns zero): norms of the centred rows x_i - mean (rbf on centred data)
 template <typename T>
-__global__ void __launch_bounds__(256) row_norms_kernel(const T *__restrict__ X, const std::size_t N, const std::uint32_t ld, T *__restrict__ sq) {
+__global__ void __launch_bounds__(256) row_norms_kernel(const T *__restrict__ X, const std::size_t N, const std::uint32_t ld, T *__restrict__ sq, const T *__restrict__ mean) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= N) { return; }
     const int lane = threadIdx.x & 31;
     const T *x = X + row * ld;
     T s0 = T(0), s1 = T(0);
     for (std::uint32_t k = 2 * lane; k < ld; k += 64) {  // ld is a multiple of 16 elements; pad columns are zero
-        s0 = pb_fma(x[k], x[k], s0);
-        s1 = pb_fma(x[k + 1], x[k + 1], s1);
+        const T a = mean != nullptr ? x[k] - mean[k] : x[k], b = mean != nullptr ? x[k + 1] - mean[k + 1] : x[k + 1];
+        s0 = pb_fma(a, a, s0);
+        s1 = pb_fma(b, b, s1);
     }
     const T s = warp_sum(s0 + s1);
     if (lane == 0) { sq[row] = s; }
+}
+
+// dst = src - mean (row-wise; pad columns stay zero because mean's pad entries are zero); dst may alias src.
+// Materialised centred copy for the tile kernels that read X itself (DMMA / 3xTF32 / SIMT); the int8-slice path centres on the fly in split_i8_kernel.
+template <typename T>
+__global__ void center_rows_kernel(const T *__restrict__ src, T *__restrict__ dst, const std::size_t N, const std::uint32_t ld, const T *__restrict__ mean) {
+    const std::size_t total = N * ld;
+    for (std::size_t idx = static_cast<std::size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += static_cast<std::size_t>(gridDim.x) * blockDim.x) {
+        dst[idx] = src[idx] - mean[idx % ld];
+    }
+}
+
+// v *= a  (feature means from the column sums)
+template <typename T>
+__global__ void scale_vec_kernel(T *__restrict__ v, const T a, const std::uint32_t n) {
+    const std::uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { v[i] *= a; }
 }
 
 // run_q_kernel (reference q_kernel.cu:16-47, CPU twin q_kernel.cpp:18-52): q[i] = k(x_i, x_last) for ALL N rows
@@ -321,7 +340,7 @@ __global__ void __launch_bounds__(256) w_partial_kernel(const T *__restrict__ SV
     const std::size_t r1 = r0 + W_ROWS < n_sv ? r0 + W_ROWS : n_sv;
     if (f >= d) { return; }
     T s = T(0);
-    for (std::size_t i = r0; i < r1; ++i) { s = pb_fma(alpha[i], SV[i * ld + f], s); }
+    for (std::size_t i = r0; i < r1; ++i) { s = pb_fma(alpha != nullptr ? alpha[i] : T(1), SV[i * ld + f], s); }  // alpha == NULL: plain column sums
     part[static_cast<std::size_t>(blockIdx.y) * d + f] = s;
 }
 // stage 2: 32 features x 8 chunk groups per block; every group adds its chunks in order, the 8 group sums are added in order

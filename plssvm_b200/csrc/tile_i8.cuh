@@ -98,10 +98,12 @@ __host__ __device__ __forceinline__ std::size_t i8_boxed_offset(const std::size_
     return (((r / BR) * num_slabs + (k >> 6)) * S + p) * (static_cast<std::size_t>(BR) * 64u) + rr * 64u + ((((kk >> 4) ^ ((rr >> 1) & 3u)) << 4) | (kk & 15u));
 }
 
+// `mean` (optional, ld entries, pad columns zero): the digits are those of x - mean, rounded once to T — the rbf kernel is evaluated on data
+// centred at the feature means of the training set / support vectors (exact translation invariance).
 template <typename T, int S>
 __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
                                                        std::int8_t *__restrict__ planes_a, std::int8_t *__restrict__ planes_b, const std::uint32_t br_b,
-                                                       const std::uint32_t num_slabs, T *__restrict__ rscale, int *__restrict__ bad_rows) {
+                                                       const std::uint32_t num_slabs, T *__restrict__ rscale, int *__restrict__ bad_rows, const T *__restrict__ mean) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (rows + TILE - 1) / TILE * TILE) { return; }
     const bool pad_row = row >= rows;  // padding rows of the last 128-row box: all digits zero
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
     const T *x = X + (pad_row ? 0 : row) * ld;
     double mx = 0.0, poison = 0.0;
     for (std::uint32_t k = lane; k < (pad_row ? 0u : d); k += 32) {
-        const double ax = fabs(static_cast<double>(x[k]));
+        const double ax = fabs(static_cast<double>(mean != nullptr ? x[k] - mean[k] : x[k]));
         mx = fmax(mx, ax);
         poison += ax * 0.0;  // NaN iff the row holds an inf or a NaN
     }
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
         long long v[4];
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const double xv = (k0 + j < d && !bad) ? static_cast<double>(x[k0 + j]) : 0.0;
+            const double xv = (k0 + j < d && !bad) ? static_cast<double>(mean != nullptr ? x[k0 + j] - mean[k0 + j] : x[k0 + j]) : 0.0;
             n_nonzero += xv != 0.0 ? 1u : 0u;
             n_small += (xv != 0.0 && fabs(xv) < small) ? 1u : 0u;
             v[j] = __double2ll_rn(xv * to_fixed);
@@ -289,23 +291,34 @@ tile_kernel_i8(const TileParams<T> p) {
                 // padding tiles of a super-tile (CL = 4, odd tile counts) load the last valid block instead of running past the buffers
                 const std::uint32_t Il = I < p.T_rows ? I : p.T_rows - 1, Jl = J < p.T_cols ? J : p.T_cols - 1;
                 for (int h = 0; h < UNITS; ++h) {
+                    // ONE copy of the digit planes serves both operands: boxes of 128 rows, plane-major.  The B operand of a unit is the
+                    // row half h of every plane of column block J's box — S pieces of NH x 64 bytes (whole 128-byte lines) when NH < 128
                     const std::int8_t *src_a = p.A_i8 + static_cast<std::size_t>(Il) * num_slabs * L8::A_BYTES;
-                    const std::int8_t *src_b = p.B_i8 + (static_cast<std::size_t>(Jl) * UNITS + h) * num_slabs * L8::B_BYTES;
+                    const std::int8_t *src_b = p.B_i8 + static_cast<std::size_t>(Jl) * num_slabs * L8::A_BYTES + h * L8::B_SLICE;
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
                         mbar_wait(empty0 + 8 * stage, phase ^ 1u);
                         const std::uint32_t dst = smem_u32(stages + stage * L8::STAGE_BYTES);
                         const std::uint32_t bar = full0 + 8 * stage;
                         mbar_arrive_expect_tx(bar, L8::STAGE_BYTES);
+                        const std::int8_t *box_a = src_a + static_cast<std::size_t>(ks) * L8::A_BYTES, *box_b = src_b + static_cast<std::size_t>(ks) * L8::A_BYTES;
                         if constexpr (CL == 1) {
-                            bulk_load(dst, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES, L8::A_BYTES, bar);
-                            bulk_load(dst + L8::A_BYTES, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES, L8::B_BYTES, bar);
+                            bulk_load(dst, box_a, L8::A_BYTES, bar);
+                            if constexpr (UNITS == 1) {
+                                bulk_load(dst + L8::A_BYTES, box_b, L8::B_BYTES, bar);
+                            } else {
+                                #pragma unroll
+                                for (int pl = 0; pl < S; ++pl) { bulk_load(dst + L8::A_BYTES + pl * L8::B_SLICE, box_b + pl * L8::A_SLICE, L8::B_SLICE, bar); }
+                            }
                         } else {
                             // this CTA fetches one contiguous half of the planes of its row block / column block for itself and its mate
                             constexpr int S0 = (S + 1) / 2;
                             const int pa0 = cc == 0 ? 0 : S0, pa1 = cc == 0 ? S0 : S, pb0 = cr == 0 ? 0 : S0, pb1 = cr == 0 ? S0 : S;
-                            bulk_load_mc(dst + pa0 * L8::A_SLICE, src_a + static_cast<std::size_t>(ks) * L8::A_BYTES + pa0 * L8::A_SLICE, static_cast<std::uint32_t>((pa1 - pa0) * L8::A_SLICE), bar, mask_a);
-                            bulk_load_mc(dst + L8::A_BYTES + pb0 * L8::B_SLICE, src_b + static_cast<std::size_t>(ks) * L8::B_BYTES + pb0 * L8::B_SLICE,
-                                         static_cast<std::uint32_t>((pb1 - pb0) * L8::B_SLICE), bar, mask_b);
+                            bulk_load_mc(dst + pa0 * L8::A_SLICE, box_a + pa0 * L8::A_SLICE, static_cast<std::uint32_t>((pa1 - pa0) * L8::A_SLICE), bar, mask_a);
+                            if constexpr (UNITS == 1) {
+                                bulk_load_mc(dst + L8::A_BYTES + pb0 * L8::B_SLICE, box_b + pb0 * L8::B_SLICE, static_cast<std::uint32_t>((pb1 - pb0) * L8::B_SLICE), bar, mask_b);
+                            } else {
+                                for (int pl = pb0; pl < pb1; ++pl) { bulk_load_mc(dst + L8::A_BYTES + pl * L8::B_SLICE, box_b + pl * L8::A_SLICE, L8::B_SLICE, bar, mask_b); }
+                            }
                         }
                         if (++stage == STAGES) {
                             stage = 0;

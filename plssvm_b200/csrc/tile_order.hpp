@@ -80,4 +80,30 @@ PB_HD void rank_range(const std::uint64_t total, const int rank, const int world
     hi = total * (static_cast<std::uint64_t>(rank) + 1) / static_cast<std::uint64_t>(world);
 }
 
+
+// the same with shares proportional to weights[0 .. world) (rate-weighted shares: GPUs under a power cap run at different clocks);
+// cut points are rounded down, so the ranges tile [0, total) exactly for any weights; non-positive weights count as equal shares
+inline void weighted_range(const std::uint64_t total, const int rank, const int world, const double *weights, std::uint64_t &lo, std::uint64_t &hi) {
+    double sum = 0.0;
+    bool ok = weights != nullptr;
+    for (int g = 0; ok && g < world; ++g) {
+        ok = weights[g] > 0.0 && weights[g] < 1e300;
+        sum += weights[g];
+    }
+    if (!ok) {
+        rank_range(total, rank, world, lo, hi);
+        return;
+    }
+    double before = 0.0;
+    for (int g = 0; g < rank; ++g) { before += weights[g]; }
+    auto cut = [&](const double cum) {
+        const double c = static_cast<double>(total) * (cum / sum);
+        const std::uint64_t v = static_cast<std::uint64_t>(c < 0.0 ? 0.0 : c);
+        return v > total ? total : v;
+    };
+    lo = rank == 0 ? 0 : cut(before);
+    hi = rank == world - 1 ? total : cut(before + weights[rank]);
+    if (hi < lo) { hi = lo; }
+}
+
 }  // namespace pb
