@@ -94,7 +94,10 @@ const char *plssvm_b200_last_error(void);
  * skipped so that exactly the requested number of CG iterations runs), "balance" (0/1, default 1; several devices / ranks:
  * re-cut the tile shares every "balance_interval" (default 8) iterations in proportion to the tile-kernel rates the ranks
  * measured — GPUs under a power cap do not run at the same clock; 0 = fixed equal shares, bit-reproducible run to run),
- * "shard_upload" (0/1, default 1; several devices / ranks: each uploads 1 / world of the rows, NCCL all-gather) */
+ * "shard_upload" (0/1, default 1; several devices / ranks: each uploads 1 / world of the rows, NCCL all-gather);
+ * testing aid on ONE device: "virtual_world" = G, "virtual_rank" = g make the context compute rank g's share of a G-rank run without
+ * a communicator — the matvec returns the partial result of rank g's tiles (the G partial results add up to the full product),
+ * predict writes only rank g's range of points; "virtual_skew" = p makes the tile shares unequal (+- p / 2 percent) */
 int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long value);
 int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out);
 /* residual history of the last finished solve: out[k] = r.r after k iterations (k = 0: r0.r0), at most 4097 entries; what the

@@ -14,6 +14,7 @@
 #include "plssvm/parameter.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstddef>
 #include <cstring>
 #include <exception>
@@ -83,6 +84,23 @@ int refb_fit_f64(const int backend, const double *X, const std::size_t N, const 
         std::copy(model.weights().begin(), model.weights().end(), alpha_out);
         *rho_out = model.rho();
         if (model_path != nullptr && model_path[0] != '\0') { model.save(model_path); }
+    });
+}
+
+// the same, timing csvm::fit alone (seconds_out[0]) and the construction of the reference's data_set before it (seconds_out[1]): bench.py's `e2e_csvm`
+int refb_fit_timed_f64(const int backend, const double *X, const std::size_t N, const std::size_t d, const int *labels, const int kernel, const int degree, const double gamma,
+                       const double coef0, const double cost, const double eps, const unsigned long long max_iter, double *alpha_out, double *rho_out, double *seconds_out) {
+    return guarded([&] {
+        const auto t0 = std::chrono::steady_clock::now();
+        const plssvm::data_set<double, int> data{ rows(X, N, d), std::vector<int>(labels, labels + N) };
+        const auto svm = make_backend(backend, make_params(kernel, degree, gamma, coef0, cost));
+        const auto t1 = std::chrono::steady_clock::now();
+        const plssvm::model<double, int> model = svm->fit(data, plssvm::epsilon = eps, plssvm::max_iter = max_iter);
+        const auto t2 = std::chrono::steady_clock::now();
+        std::copy(model.weights().begin(), model.weights().end(), alpha_out);
+        *rho_out = model.rho();
+        seconds_out[0] = std::chrono::duration<double>(t2 - t1).count();
+        seconds_out[1] = std::chrono::duration<double>(t1 - t0).count();
     });
 }
 

@@ -206,3 +206,92 @@ class RefCuda:
         if rc != 0:
             raise RuntimeError(f"refcuda_matvec failed with code {rc}")
         return out, float(ms.value)
+
+
+class Exact:
+    """The extended-precision, deterministic restatement of the same algorithm (oracle/lssvm_exact.cpp -> liboracle_exact.so):
+    compensated dot products (twice the working precision) + long double everywhere else.  Results come back as float64.
+    It is the noise-free target: parity is judged by |repo - exact| against |reference - exact| (tests/parity.py)."""
+
+    PATH = os.path.join(_HERE, "liboracle_exact.so")
+
+    def __init__(self):
+        if not os.path.exists(self.PATH):
+            build(("exact",))
+        self.lib = ctypes.CDLL(self.PATH)
+        vp, sz, i32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_uint64
+        for suf, ct in (("f32", ctypes.c_float), ("f64", ctypes.c_double)):
+            getattr(self.lib, f"exact_solve_{suf}").argtypes = [i32, vp, sz, sz, vp, i32, ct, ct, ct, ct, u64, vp, vp, vp, vp]
+            getattr(self.lib, f"exact_solve_{suf}").restype = i32
+            getattr(self.lib, f"exact_matvec_{suf}").argtypes = [i32, vp, sz, sz, vp, vp, ct, ct, i32, ct, ct, vp, sz, vp]
+            getattr(self.lib, f"exact_matvec_{suf}").restype = None
+            getattr(self.lib, f"plain_matvec_{suf}").argtypes = [i32, vp, sz, sz, vp, vp, ct, ct, i32, ct, ct, vp, sz, vp]
+            getattr(self.lib, f"plain_matvec_{suf}").restype = None
+            getattr(self.lib, f"exact_q_{suf}").argtypes = [i32, vp, sz, sz, i32, ct, ct, vp]
+            getattr(self.lib, f"exact_q_{suf}").restype = None
+            getattr(self.lib, f"exact_predict_{suf}").argtypes = [i32, vp, sz, sz, vp, ct, vp, sz, i32, ct, ct, vp]
+            getattr(self.lib, f"exact_predict_{suf}").restype = None
+
+    @staticmethod
+    def _prep(X):
+        X = np.ascontiguousarray(X)
+        if X.dtype not in (np.float32, np.float64):
+            raise TypeError("real_type must be float32 or float64")
+        return X, ("f32" if X.dtype == np.float32 else "f64")
+
+    def solve(self, kernel: int, X, y, degree=3, gamma=1.0, coef0=0.0, cost=1.0, eps=1e-3, max_iter=None):
+        """CG in extended precision with the reference's stopping rule; pin `max_iter` to compare at an equal iteration count."""
+        X, suf = self._prep(X)
+        N, d = X.shape
+        y = np.ascontiguousarray(y, dtype=X.dtype)
+        max_iter = N if max_iter is None else int(max_iter)
+        alpha, rho, iters, trace = np.empty(N), np.zeros(1), np.zeros(1, dtype=np.uint64), np.zeros(max_iter + 1)
+        rc = getattr(self.lib, f"exact_solve_{suf}")(kernel, X.ctypes.data, N, d, y.ctypes.data, int(degree), gamma, coef0, cost, eps, max_iter, alpha.ctypes.data,
+                                                     rho.ctypes.data, iters.ctypes.data, trace.ctypes.data)
+        if rc != 0:
+            raise ValueError("invalid arguments")
+        return {"alpha": alpha, "rho": float(rho[0]), "iterations": int(iters[0]), "trace": trace[: int(iters[0]) + 1].copy()}
+
+    def matvec(self, kernel: int, X, q, v, QA_cost, cost_inv, degree=3, gamma=1.0, coef0=0.0, rows=None) -> np.ndarray:
+        """Rows `rows` (default: all) of Q~ v for q, v, QA_cost given in the real type of X (the run_svm_kernel argument convention, add = +1, ret = 0)."""
+        X, suf = self._prep(X)
+        N, d = X.shape
+        q = np.ascontiguousarray(q, dtype=X.dtype)
+        v = np.ascontiguousarray(v, dtype=X.dtype)
+        if rows is None:
+            out = np.empty(N - 1)
+            getattr(self.lib, f"exact_matvec_{suf}")(kernel, X.ctypes.data, N, d, q.ctypes.data, v.ctypes.data, QA_cost, cost_inv, int(degree), gamma, coef0, None, 0, out.ctypes.data)
+        else:
+            rows = np.ascontiguousarray(rows, dtype=np.uint64)
+            out = np.empty(rows.size)
+            getattr(self.lib, f"exact_matvec_{suf}")(kernel, X.ctypes.data, N, d, q.ctypes.data, v.ctypes.data, QA_cost, cost_inv, int(degree), gamma, coef0, rows.ctypes.data,
+                                                     rows.size, out.ctypes.data)
+        return out
+
+    def reference_arithmetic_matvec(self, kernel: int, X, q, v, QA_cost, cost_inv, rows, degree=3, gamma=1.0, coef0=0.0) -> np.ndarray:
+        """The same rows in the reference's arithmetic (sequential FMA chains and sums in the real type of X): its rounding behaviour on sampled rows."""
+        X, suf = self._prep(X)
+        N, d = X.shape
+        q = np.ascontiguousarray(q, dtype=X.dtype)
+        v = np.ascontiguousarray(v, dtype=X.dtype)
+        rows = np.ascontiguousarray(rows, dtype=np.uint64)
+        out = np.empty(rows.size, dtype=X.dtype)
+        getattr(self.lib, f"plain_matvec_{suf}")(kernel, X.ctypes.data, N, d, q.ctypes.data, v.ctypes.data, QA_cost, cost_inv, int(degree), gamma, coef0, rows.ctypes.data, rows.size,
+                                                 out.ctypes.data)
+        return out
+
+    def q(self, kernel: int, X, degree=3, gamma=1.0, coef0=0.0) -> np.ndarray:
+        """k(x_i, x_last) for ALL N rows (the last entry is k(x_last, x_last))."""
+        X, suf = self._prep(X)
+        out = np.empty(X.shape[0])
+        getattr(self.lib, f"exact_q_{suf}")(kernel, X.ctypes.data, X.shape[0], X.shape[1], int(degree), gamma, coef0, out.ctypes.data)
+        return out
+
+    def predict(self, kernel: int, SV, alpha, rho, P, degree=3, gamma=1.0, coef0=0.0) -> np.ndarray:
+        SV, suf = self._prep(SV)
+        P = np.ascontiguousarray(P, dtype=SV.dtype)
+        alpha = np.ascontiguousarray(alpha, dtype=SV.dtype)
+        out = np.empty(P.shape[0])
+        getattr(self.lib, f"exact_predict_{suf}")(kernel, SV.ctypes.data, SV.shape[0], SV.shape[1], alpha.ctypes.data, rho, P.ctypes.data, P.shape[0], int(degree), gamma, coef0,
+                                                  out.ctypes.data)
+        return out

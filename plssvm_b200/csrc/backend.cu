@@ -412,7 +412,7 @@ constexpr int nccl_type() { return sizeof(T) == 8 ? NCCL_FLOAT64 : NCCL_FLOAT32;
 
 template <typename T>
 void all_reduce_sum(plssvm_b200_ctx *ctx, T *buf, const std::size_t count) {
-    if (ctx->world <= 1) { return; }
+    if (ctx->world <= 1 || ctx->comm == nullptr) { return; }  // (no communicator: a virtual rank, see option "virtual_world")
     const nccl_api &nccl = nccl_api::get();
     nccl.check(nccl.AllReduce(buf, buf, count, nccl_type<T>(), NCCL_SUM, ctx->comm, ctx->stream), "ncclAllReduce");
 }
@@ -475,7 +475,10 @@ struct matvec_plan {
         tile_shift = super_tiled(impl) ? 1 : 0;  // CTA-pair kernel: the schedule (and rank ownership) is over 256 x 256 super-tiles
         total_tiles = pb::tri_num_tiles((Tb + tile_shift) >> tile_shift);
         weights.assign(static_cast<std::size_t>(c->world), 1.0);
-        pb::rank_range(total_tiles, c->rank, c->world, tile_lo, tile_hi);
+        if (c->comm == nullptr && c->world > 1 && c->virtual_skew != 0) {  // virtual ranks: deliberately unequal shares, to test the rate-weighted cut
+            for (int g = 0; g < c->world; ++g) { weights[static_cast<std::size_t>(g)] = 1.0 + 0.01 * c->virtual_skew * (static_cast<double>(g) / (c->world - 1) - 0.5); }
+        }
+        pb::weighted_range(total_tiles, c->rank, c->world, weights.data(), tile_lo, tile_hi);
         if (tiles_needed) { partial.alloc(c, static_cast<std::size_t>(Tb) * Tb * TILE); }
         base = TileParams<T>{};
         set_operands(base, op, op);
@@ -615,13 +618,13 @@ plssvm_b200_dataset *dataset_create_rank(plssvm_b200_ctx *ctx, const host_matrix
         ds->ld = pitch_elems<T>(d);
         ds->id = g_next_dataset_id.fetch_add(1);
         const std::size_t G = static_cast<std::size_t>(ctx->world);
-        const bool sharded = G > 1 && host.valid() && ctx->shard_upload != 0;
+        const bool sharded = G > 1 && ctx->comm != nullptr && host.valid() && ctx->shard_upload != 0;
         const std::size_t share = sharded ? (N + G - 1) / G : N;  // rows per rank (the last share may be short; X is allocated for G full shares)
         const std::size_t rows_alloc = sharded ? share * G : N;
         blk_alloc(ctx, ds->X, rows_alloc * ds->ld * sizeof(T));
         blk_alloc(ctx, ds->sq, N * sizeof(T));
         T *X = static_cast<T *>(ds->X.p);
-        const nccl_api *nccl = G > 1 ? &nccl_api::get() : nullptr;
+        const nccl_api *nccl = (G > 1 && ctx->comm != nullptr) ? &nccl_api::get() : nullptr;
         if (dev_src != nullptr) {
             if (!ctx->in_process_group() || ctx->rank == 0) {
                 const std::size_t total = N * ds->ld;
@@ -792,7 +795,7 @@ struct cg_session : cg_session_base {
         ctx->tm.kernel_launches += (iter % 50 == 49) ? 6 : 5;
     }
 
-    bool balancing() const { return ctx->world > 1 && ctx->balance != 0 && !(ctx->linear_factorized != 0 && kp.kernel == pb::K_LINEAR); }
+    bool balancing() const { return ctx->world > 1 && ctx->comm != nullptr && ctx->balance != 0 && !(ctx->linear_factorized != 0 && kp.kernel == pb::K_LINEAR); }
 
     // Rate-weighted tile shares: every rank contributes the rate (tiles per ms) its tile kernels ran at since the last re-cut; the all-gathered
     // rates — identical on every rank — become the new weights of the contiguous shares of the tile order.  Ownership is recomputed from the
@@ -1177,7 +1180,7 @@ void predict_rank(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alpha,
     PB_CUDA(cudaStreamSynchronize(st));
 
     // one process per GPU: every rank returns all m values (sum of the zero-extended shares; 8 bytes per point over NVLink)
-    if (ctx->world > 1 && !ctx->in_process_group()) {
+    if (ctx->world > 1 && ctx->comm != nullptr && !ctx->in_process_group()) {
         for (std::size_t s0 = 0; s0 < m; s0 += SUPER_BATCH) {
             const std::size_t ms = std::min(SUPER_BATCH, m - s0);
             T *buf = workspace<T>(ctx, ctx_t::WS_OUT, std::min(m, SUPER_BATCH));
@@ -1472,6 +1475,19 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
             PB_REQUIRE(value >= 0 && value <= 4096, "max_ctas out of range");
         } else if (k == "balance_interval") {
             PB_REQUIRE(value >= 1 && value <= 1000000, "balance_interval out of range");
+        } else if (k == "virtual_world" || k == "virtual_rank" || k == "virtual_skew") {
+            PB_REQUIRE(ctx->comm == nullptr && ctx->members.size() <= 1, "virtual ranks are a single-device testing aid: the context must not have a communicator");
+            PB_REQUIRE(value >= 0 && value <= 64, k + " out of range");
+            if (k == "virtual_world") {
+                ctx->world = std::max(1, static_cast<int>(value));
+                ctx->rank = std::min(ctx->rank, ctx->world - 1);
+            } else if (k == "virtual_rank") {
+                PB_REQUIRE(value < ctx->world, "virtual_rank must be below virtual_world");
+                ctx->rank = static_cast<int>(value);
+            } else {
+                ctx->virtual_skew = static_cast<int>(value);
+            }
+            return;
         } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload") {
             throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
         }

@@ -170,6 +170,7 @@ struct plssvm_b200_ctx {
     int linear_factorized = 0;   // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     int balance = 1;             // several ranks: re-cut the tile shares from the measured tile-kernel rates every `balance_interval` iterations
     int balance_interval = 8;
+    int virtual_skew = 0;        // testing aid (virtual ranks): percent by which the tile shares grow from the first to the last rank
     int shard_upload = 1;        // several ranks: every rank uploads 1 / world of the rows over its own PCIe link, ncclAllGather over NVLink
     // timings of the last call (accumulated over the lifetime of an open CG session)
     plssvm_b200_timings tm{};

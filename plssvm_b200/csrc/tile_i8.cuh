@@ -19,8 +19,9 @@
 // 10 wide MMAs (N up to 256) per 32-feature step instead of 28 narrow ones, which cuts the shared-memory operand reads
 // from 168 KB to 96 KB per step (107 B/clk at the tensor pipe's pace; with the 42 KB the producer writes into the ring per step the
 // shared-memory port sees 154 B/clk against the 128 B/clk it delivers — that port, not L2 or the tensor pipe, bounds the kernel: DESIGN.md §3.0).
-//   * warp 0: producer — per 64-feature slab two contiguous bulk copies (cp.async.bulk) of pre-swizzled operand boxes: A = 128 rows x S planes
-//     (56 KB), B = 64 rows x S planes (28 KB); 2-stage ring (see split_i8_kernel for the layout in HBM)
+//   * warp 0: producer — per 64-feature slab contiguous bulk copies (cp.async.bulk) out of pre-swizzled operand boxes: A = 128 rows x S planes
+//     (56 KB, one copy), B = 64 rows x S planes (28 KB, one 4 KB piece per plane of the column block's box); 2-stage ring (see split_i8_kernel
+//     for the layout in HBM)
 //   * warp 1: allocates all 512 TMEM columns (S x 64 int32 accumulator columns) and issues the MMAs from one elected lane
 //   * warps 2-9: epilogue, one accumulator row and 32 columns per thread: tcgen05.ld, int32 -> fp64 without I2F (exponent
 //     trick), Horner recombination, hand TMEM back to the MMA warp, then kernel function, QA_cost - q_i - q_j (+ 1/C on the
@@ -83,8 +84,9 @@ struct I8Layout {
 // copies (cp.async.bulk, whole 128-byte lines) instead of 2-D / 3-D tensor boxes whose 64-byte rows halve TMA's request efficiency:
 //     box(R, ks) = all S planes of the BR rows [R BR, (R+1) BR) and the 64 features [64 ks, 64 ks + 64):  S x BR x 64 bytes, plane-major;
 //     offset(p, r, k) = (((r / BR) num_slabs + k / 64) S + p) BR 64 + (r % BR) 64 + ((((k % 64) / 16) ^ (((r % BR) / 2) % 4)) 16) + k % 16
-// The A operand (tile rows) uses BR = 128; the B operand (unit columns) BR = br_b = rows staged per CTA (fp64: 64 — a second copy; fp32: 128 — the
-// same buffer — or 64 for the CTA-pair kernel of tile_i8_2sm.cuh).
+// ONE copy with BR = 128 serves both operands: the A operand of a tile is a whole box, the B operand of a 128 x NH unit is the row range
+// [h NH, (h + 1) NH) of every plane of a box — S contiguous pieces of NH x 64 bytes (fp64: NH = 64, seven 4 KiB pieces; fp32: NH = 128, the whole
+// box).  planes_b / br_b: an optional second copy in boxes of br_b rows, written only for the experimental CTA-pair kernel of tile_i8_2sm.cuh.
 // Rows are padded to a multiple of 128 and features to a multiple of 64 with zero digits (written by this kernel: launch it over the padded rows).
 // rscale[row] = 2^(e_row - 6); one warp per row.
 // The products are accurate to ~2^-(8S-2) sqrt(d) |x_i| |x_j| whatever the data (the fixed-point grid is relative to the row maximum,
@@ -410,7 +412,12 @@ tile_kernel_i8(const TileParams<T> p) {
                     s_col[3 * NH + c] = okj ? p.B_scale[gj] : T(0);
                 }
                 named_bar_sync(1, I8_EPI_THREADS);
-                const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row], sci = s_row[3 * TILE + row];
+                const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row];
+                // fp32, S = 3, d <= 1984: the two upper diagonals fit one int32 (|ACC_2| 2^8 + |ACC_1| <= d (2^20 + 2^14) < 2^31), so the recombination
+                // costs one IMAD + 3 instead of 5 fp64 operations per element (the fp64 pipe, 64 / clk / SM, paces the TMEM drain of the fp32 kernel);
+                // the sum is 256 x the value, folded into the row scale.  Both forms are exact in fp64: bit-identical results.
+                const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;
+                const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
 
                 mbar_wait(tfull, unit_iter & 1u);
                 tcgen05_fence_after();
@@ -425,12 +432,20 @@ tile_kernel_i8(const TileParams<T> p) {
                     #pragma unroll
                     for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
                     tmem_ld_wait();
-                    #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        double s = i32_to_f64(r[0][j]);
+                    if (fold3) {
                         #pragma unroll
-                        for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
-                        a[g * 8 + j] = static_cast<T>(s);
+                        for (int j = 0; j < 8; ++j) {
+                            const std::uint32_t hi = r[S - 1][j] * 256u + r[S >= 2 ? S - 2 : 0][j];
+                            a[g * 8 + j] = static_cast<T>(fma(i32_to_f64(r[0][j]), 0.00390625, i32_to_f64(hi)));
+                        }
+                    } else {
+                        #pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            double s = i32_to_f64(r[0][j]);
+                            #pragma unroll
+                            for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
+                            a[g * 8 + j] = static_cast<T>(s);
+                        }
                     }
                 }
                 // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp

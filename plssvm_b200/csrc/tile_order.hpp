@@ -90,7 +90,9 @@ inline void weighted_range(const std::uint64_t total, const int rank, const int 
         ok = weights[g] > 0.0 && weights[g] < 1e300;
         sum += weights[g];
     }
-    if (!ok) {
+    bool equal = ok;
+    for (int g = 1; equal && g < world; ++g) { equal = weights[g] == weights[0]; }
+    if (!ok || equal) {  // equal weights: exactly the integer split
         rank_range(total, rank, world, lo, hi);
         return;
     }

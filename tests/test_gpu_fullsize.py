@@ -40,6 +40,17 @@ def orc():
     return oracle.Oracle("reference" if oracle.available("reference") else "port")
 
 
+def _report(key, entry):
+    """Accumulates gpurun_out/parity_report_fullsize.json (committed under profiles/ after the run)."""
+    import json
+    path = os.path.join(ROOT, "gpurun_out", "parity_report_fullsize.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[key] = entry
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1, sort_keys=True)
+
+
 def _kernel_rows_torch(X, rows, kernel, gamma, degree=3, coef0=0.0):
     """k(x_i, x_j) for i in rows, all j < n, by torch fp64 (cuBLAS) — independent of the library under test."""
     import torch
@@ -104,6 +115,20 @@ def test_full_size_matvec_row_sampled(be, orc, workload):
         Kr_t = K[(rows == r).nonzero()[0, 0]][torch.from_numpy(sample_cols).to(dev)].cpu().numpy()
         assert np.max(np.abs(kr - Kr_t)) <= tol * max(1.0, np.max(np.abs(kr)))
         assert abs(orc.kernel_function(KERNEL_IDS[kernel], xr, x_last, gamma=gamma) - q[r]) <= tol * max(1.0, abs(q[r]))
+
+    # (c) 8 rows against the extended-precision target (oracle/lssvm_exact.cpp), next to the same rows in the reference's arithmetic
+    # (sequential FMA chains in the real type): |repo - exact| must be at the reference's level — numbers go to gpurun_out/parity_report_fullsize.json
+    ex = oracle.Exact()
+    Xh = X.cpu().numpy()
+    rows8 = np.sort(rng.choice(n, 8, replace=False))
+    exact = ex.matvec(KERNEL_IDS[kernel], Xh, q, v, qa, 1.0 / cost, gamma=gamma, rows=rows8)
+    plain = ex.reference_arithmetic_matvec(KERNEL_IDS[kernel], Xh, q, v, qa, 1.0 / cost, rows8, gamma=gamma)
+    del Xh
+    sc = float(np.max(np.abs(exact)))
+    repo_err = float(np.max(np.abs(Qv[rows8].astype(np.float64) - exact))) / sc
+    ref_err = float(np.max(np.abs(plain.astype(np.float64) - exact))) / sc
+    _report(workload, {"rows_sampled": 8, "matvec_err_vs_exact": repo_err, "reference_arithmetic_err_vs_exact": ref_err, "kernel": kernel, "dtype": dtype, "tile_impl": int(t["impl_used"])})
+    assert repo_err <= max(8 * np.finfo(npdt).eps, 2.0 * ref_err), (workload, repo_err, ref_err)
 
     # symmetry and linearity on the full vectors
     Qu = be.run_svm_kernel(ds, q, u, z, qa, 1.0 / cost, 1.0, kernel, gamma=gamma)

@@ -89,3 +89,23 @@ def test_two_rank_sharded_matvec_matches_oracle(kernel):
     assert abs(counts[0] - counts[1]) <= 1 and sum(counts) == pb.tri_num_tiles((699 + 127) // 128)
     for _, _, err in res:
         assert err < 1e-12
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_weighted_ranges_tile_the_order_exactly(world):
+    """Rate-weighted shares (option "balance"): whatever the weights, the ranks' ranges are contiguous, ordered and cover every tile exactly once;
+    equal weights reproduce rank_range; degenerate weights fall back to equal shares."""
+    rng = np.random.default_rng(world)
+    for total in (0, 1, 7, 131328, 10 ** 9 + 7):
+        for weights in ([1.0] * world, list(rng.uniform(0.75, 1.25, world)), list(rng.uniform(0.01, 5.0, world))):
+            edges = [pb.weighted_range(total, g, world, weights) for g in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(lo <= hi for lo, hi in edges) and all(edges[g][1] == edges[g + 1][0] for g in range(world - 1))
+            if len(set(weights)) == 1:
+                assert edges == [pb.rank_range(total, g, world) for g in range(world)]
+            elif total > 1000 * world:
+                shares = np.array([hi - lo for lo, hi in edges], dtype=float) / total
+                assert np.allclose(shares, np.array(weights) / np.sum(weights), atol=2.0 / total + 1e-12)
+        bad = [1.0] * world
+        bad[-1] = 0.0
+        assert [pb.weighted_range(total, g, world, bad) for g in range(world)] == [pb.rank_range(total, g, world) for g in range(world)]
