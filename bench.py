@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short extra workloads (C1 / C3 / C4 factorised / C5) the default N = 1 run appends")
     ap.add_argument("--no-through-csvm", action="store_true", help="skip the second end-to-end number through the reference's csvm::fit (integration/ref_bridge)")
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE", help="extra plssvm_b200_set_option settings (development / A-B measurements)")
     ap.add_argument("--balance", type=int, default=1, help="several ranks: rate-weighted tile shares (1, default) or fixed equal shares (0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="CPU work budget of the cpu_baseline sample")
@@ -277,6 +278,9 @@ class Ranks:
         if args.tile_impl:
             be.set_option("impl", args.tile_impl)
         be.set_option("balance", args.balance)
+        for kv in args.option:
+            key, val = kv.split("=")
+            be.set_option(key, int(val))
         if self.world > 1:
             be.init_comm_from_torch()
         return be

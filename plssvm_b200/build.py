@@ -31,9 +31,12 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """PLSSVM_B200_EXPERIMENTAL=1 in the environment adds -DPLSSVM_B200_EXPERIMENTAL: the measured-but-not-faster tile-kernel variants
+    (impl 4 / 5 / 8 / 9) are compiled in as well.  The default library does not contain them."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    experimental = ["-DPLSSVM_B200_EXPERIMENTAL"] if os.environ.get("PLSSVM_B200_EXPERIMENTAL", "0") not in ("", "0") else []
+    cmd = [_nvcc(), *NVCC_FLAGS, *experimental, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     env = dict(os.environ)
     env.pop("CXX", None)  # the image's CXX points at a compiler wrapper without OpenMP specs; nvcc should use the distro g++
     res = subprocess.run(cmd, env=env, capture_output=True, text=True)

@@ -27,6 +27,8 @@
 #endif
 
 #include <cmath>
+#include <mutex>
+#include <unordered_set>
 
 using namespace pbrt;
 
@@ -67,6 +69,24 @@ using pb::TileParams;
 using pb::TILE;
 
 std::atomic<std::uint64_t> g_next_dataset_id{ 1 };
+
+// Live handles (contexts, data sets, CG sessions).  Destroying a context destroys the data sets and sessions created from it; a later
+// destroy / abort of such a handle (e.g. from a garbage collector that runs finalisers in any order) is a no-op instead of a use-after-free,
+// and any other use of a dead handle is reported as an error.
+std::mutex g_handles_mutex;
+std::unordered_set<const void *> g_live_handles;
+void handle_add(const void *h) {
+    const std::lock_guard<std::mutex> lock(g_handles_mutex);
+    g_live_handles.insert(h);
+}
+bool handle_remove(const void *h) {
+    const std::lock_guard<std::mutex> lock(g_handles_mutex);
+    return g_live_handles.erase(h) > 0;
+}
+bool handle_live(const void *h) {
+    const std::lock_guard<std::mutex> lock(g_handles_mutex);
+    return h != nullptr && g_live_handles.count(h) > 0;
+}
 
 void blk_alloc(plssvm_b200_ctx *ctx, dblock &b, const std::size_t bytes) {
     if (b.p != nullptr) { pool_release(ctx, b.p, b.bytes); }
@@ -398,8 +418,10 @@ int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
 inline bool i8_forced(const plssvm_b200_ctx *ctx) { return is_i8(ctx->impl); }
 
 template <typename T, int MODE>
-void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl) {
+void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p_in, const int impl) {
     ctx->tm.impl_used = impl;
+    TileParams<T> p = p_in;
+    p.slow_drain = ctx->fp32_fast_drain != 0 ? 0 : 1;
     switch (p.kp.kernel) {
         case pb::K_LINEAR: launch_tiles_t<T, pb::K_LINEAR, MODE>(ctx, p, impl); break;
         case pb::K_POLYNOMIAL: launch_tiles_t<T, pb::K_POLYNOMIAL, MODE>(ctx, p, impl); break;
@@ -665,7 +687,7 @@ void dataset_destroy_rank(plssvm_b200_dataset *ds) {
 // creates the data set on every device of the context; returns the handle (member 0)
 template <typename T>
 plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const host_matrix<T> &host, const T *dev_src, const std::size_t N, const std::size_t d) {
-    PB_REQUIRE(ctx != nullptr, "context is NULL");
+    PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");
     const std::size_t G = std::max<std::size_t>(1, ctx->members.size());
     std::vector<plssvm_b200_dataset *> parts(G, nullptr);
     try {
@@ -675,11 +697,15 @@ plssvm_b200_dataset *dataset_create(plssvm_b200_ctx *ctx, const host_matrix<T> &
         throw;
     }
     if (G > 1) { parts[0]->members = parts; }
+    ctx->live_datasets.push_back(parts[0]);
+    handle_add(parts[0]);
     return parts[0];
 }
 
 void dataset_destroy(plssvm_b200_dataset *ds) {
-    if (ds == nullptr) { return; }
+    if (!handle_remove(ds)) { return; }  // NULL, or already destroyed together with its context
+    auto &live = ds->ctx->live_datasets;
+    live.erase(std::remove(live.begin(), live.end(), ds), live.end());
     const std::vector<plssvm_b200_dataset *> members = ds->members;
     if (members.size() > 1) {
         for (auto *m : members) { dataset_destroy_rank(m); }
@@ -691,6 +717,8 @@ void dataset_destroy(plssvm_b200_dataset *ds) {
 plssvm_b200_dataset *member_of(plssvm_b200_dataset *ds, const int g) { return ds->members.size() > 1 ? ds->members[static_cast<std::size_t>(g)] : ds; }
 
 void check_group_dataset(const plssvm_b200_ctx *ctx, const plssvm_b200_dataset *ds, const std::size_t elem, const char *what) {
+    PB_REQUIRE(handle_live(ctx), "the context is NULL or has been destroyed");
+    PB_REQUIRE(handle_live(ds), std::string(what) + " dataset is NULL or has been destroyed (data sets die with their context)");
     check_dataset(ctx, ds, elem, what);
     PB_REQUIRE(ds->members.size() == ctx->members.size() || (ds->members.empty() && ctx->members.size() <= 1), std::string(what) + " dataset was not created by this context");
 }
@@ -769,6 +797,7 @@ struct cg_session : cg_session_base {
         pb::cg_update_d_kernel<T, true><<<vblocks, pb::VEC_BLOCK, 0, st>>>(dvec.p, r.p, n, state.p);
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += 3;
+        PB_CUDA(cudaStreamSynchronize(st));  // (the event timers below assume that everything recorded before an iteration chunk has completed)
         ctx->open_sessions++;
         counted = true;
     }
@@ -1382,6 +1411,25 @@ struct plssvm_b200_cg {
     std::vector<std::unique_ptr<cg_session_base>> ranks;  // one session per device of the context
 };
 
+namespace {
+
+// frees a CG session handle (idempotent through the handle registry)
+void cg_release(plssvm_b200_cg *cg) {
+    if (!handle_remove(cg)) { return; }
+    auto &live = cg->ctx->live_sessions;
+    live.erase(std::remove(live.begin(), live.end(), cg), live.end());
+    for (auto &s : cg->ranks) {
+        if (s != nullptr) {
+            cudaSetDevice(s->ctx->device);
+            cudaStreamSynchronize(s->ctx->stream);
+            s.reset();
+        }
+    }
+    delete cg;
+}
+
+}  // namespace
+
 extern "C" {
 
 const char *plssvm_b200_last_error(void) { return g_last_error.c_str(); }
@@ -1435,13 +1483,18 @@ int plssvm_b200_create(const int *device_ids, int n_dev, plssvm_b200_ctx **out) 
             throw;
         }
         PB_CUDA(cudaSetDevice(members[0]->device));
+        handle_add(members[0]);
         *out = members[0];
     });
 }
 
 int plssvm_b200_destroy(plssvm_b200_ctx *ctx) {
     return guarded([&] {
-        if (ctx == nullptr) { return; }
+        if (!handle_live(ctx)) { return; }  // NULL or already destroyed
+        // sessions and data sets created from this context die with it (their handles become no-ops)
+        while (!ctx->live_sessions.empty()) { cg_release(ctx->live_sessions.back()); }
+        while (!ctx->live_datasets.empty()) { dataset_destroy(ctx->live_datasets.back()); }
+        handle_remove(ctx);
         const std::vector<plssvm_b200_ctx *> members = ctx->members;
         if (members.size() > 1) {
             for (auto *m : members) { destroy_device_context(m); }
@@ -1453,14 +1506,14 @@ int plssvm_b200_destroy(plssvm_b200_ctx *ctx) {
 
 int plssvm_b200_num_devices(const plssvm_b200_ctx *ctx, int *count) {
     return guarded([&] {
-        PB_REQUIRE(ctx != nullptr && count != nullptr, "ctx or count is NULL");
+        PB_REQUIRE(handle_live(ctx) && count != nullptr, "ctx (NULL or destroyed) or count is NULL");
         *count = static_cast<int>(std::max<std::size_t>(1, ctx->members.size()));
     });
 }
 
 int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long value) {
     return guarded([&] {
-        PB_REQUIRE(ctx != nullptr && key != nullptr, "ctx or key is NULL");
+        PB_REQUIRE(handle_live(ctx) && key != nullptr, "ctx (NULL or destroyed) or key is NULL");
         const std::string k(key);
         if (k == "impl") {
             const bool known = value == 0 || value == 1 || value == 2 || value == 6 || value == 7 || (EXPERIMENTAL && (value == 4 || value == 5 || value == 8 || value == 9));
@@ -1488,7 +1541,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 ctx->virtual_skew = static_cast<int>(value);
             }
             return;
-        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload") {
+        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain") {
             throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
         }
         for_all_members(ctx, [&](plssvm_b200_ctx *c) {
@@ -1510,6 +1563,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 c->balance_interval = static_cast<int>(value);
             } else if (k == "shard_upload") {
                 c->shard_upload = value != 0;
+            } else if (k == "fp32_fast_drain") {
+                c->fp32_fast_drain = value != 0;
             }
         });
     });
@@ -1517,7 +1572,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
 
 int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out) {
     return guarded([&] {
-        PB_REQUIRE(ctx != nullptr && out != nullptr, "ctx or out is NULL");
+        PB_REQUIRE(handle_live(ctx) && out != nullptr, "ctx (NULL or destroyed) or out is NULL");
         *out = ctx->tm;
         // device group: device times are the maximum over the devices, byte and launch counts the sums
         for (std::size_t g = 1; g < ctx->members.size(); ++g) {
@@ -1536,7 +1591,7 @@ int plssvm_b200_get_timings(const plssvm_b200_ctx *ctx, plssvm_b200_timings *out
 
 int plssvm_b200_last_trace(const plssvm_b200_ctx *ctx, double *out, size_t capacity, size_t *count) {
     return guarded([&] {
-        PB_REQUIRE(ctx != nullptr && count != nullptr && (out != nullptr || capacity == 0), "ctx, out or count is NULL");
+        PB_REQUIRE(handle_live(ctx) && count != nullptr && (out != nullptr || capacity == 0), "ctx (NULL or destroyed), out or count is NULL");
         const std::size_t n = std::min(capacity, ctx->last_trace.size());
         std::copy(ctx->last_trace.begin(), ctx->last_trace.begin() + static_cast<std::ptrdiff_t>(n), out);
         *count = n;
@@ -1555,7 +1610,7 @@ int plssvm_b200_comm_unique_id(void *id128) {
 
 int plssvm_b200_comm_init(plssvm_b200_ctx *ctx, int rank, int world_size, const void *id128) {
     return guarded([&] {
-        PB_REQUIRE(ctx != nullptr, "context is NULL");
+        PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");
         PB_REQUIRE(ctx->members.size() <= 1, "plssvm_b200_comm_init is for single-device contexts (one process per GPU); this context already drives several devices");
         PB_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "invalid rank / world size");
         if (world_size == 1) {
@@ -1593,7 +1648,7 @@ int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {
 
 int plssvm_b200_cg_step(plssvm_b200_cg *cg, uint64_t iterations, uint64_t *iterations_done, int *converged) {
     return guarded([&] {
-        PB_REQUIRE(cg != nullptr && !cg->ranks.empty(), "cg session is NULL");
+        PB_REQUIRE(handle_live(cg) && !cg->ranks.empty(), "cg session is NULL or has been finished / aborted / destroyed with its context");
         for_each_rank(cg->ctx, [&](plssvm_b200_ctx *, const int g) {
             if (cg->elem_size == 8) {
                 static_cast<cg_session<double> *>(cg->ranks[g].get())->step(iterations);
@@ -1614,17 +1669,7 @@ int plssvm_b200_cg_step(plssvm_b200_cg *cg, uint64_t iterations, uint64_t *itera
 }
 
 int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
-    return guarded([&] {
-        if (cg == nullptr) { return; }
-        for (auto &s : cg->ranks) {
-            if (s != nullptr) {
-                cudaSetDevice(s->ctx->device);
-                cudaStreamSynchronize(s->ctx->stream);
-                s.reset();
-            }
-        }
-        delete cg;
-    });
+    return guarded([&] { cg_release(cg); });
 }
 
 #define PB_INSTANTIATE(SUF, T)                                                                                                                                                   \
@@ -1644,7 +1689,7 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     }                                                                                                                                                                            \
     int plssvm_b200_cg_begin_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps, plssvm_b200_cg **out) { \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr && out != nullptr, "context or out is NULL");                                                                                              \
+            PB_REQUIRE(handle_live(ctx) && out != nullptr, "context (NULL or destroyed) or out is NULL");                                                                                              \
             check_group_dataset(ctx, X, sizeof(T), "training");                                                                                                                  \
             for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                  \
             auto holder = std::make_unique<plssvm_b200_cg>();                                                                                                                    \
@@ -1655,32 +1700,36 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
                 holder->ranks[g] = std::make_unique<cg_session<T>>(c, member_of(X, g), y, kernel, degree, gamma, coef0, cost, eps);                                              \
                 PB_CUDA(cudaStreamSynchronize(c->stream));                                                                                                                       \
             });                                                                                                                                                                  \
+            ctx->live_sessions.push_back(holder.get());                                                                                                                          \
+            handle_add(holder.get());                                                                                                                                            \
             *out = holder.release();                                                                                                                                             \
         });                                                                                                                                                                      \
     }                                                                                                                                                                            \
     int plssvm_b200_cg_trace_##SUF(plssvm_b200_cg *cg, T *out, size_t capacity, size_t *count) {                                                                                \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(cg != nullptr && !cg->ranks.empty() && out != nullptr && count != nullptr, "cg session, out or count is NULL");                                           \
+            PB_REQUIRE(handle_live(cg) && !cg->ranks.empty() && out != nullptr && count != nullptr, "cg session (NULL or no longer alive), out or count is NULL");               \
             PB_REQUIRE(cg->elem_size == static_cast<int>(sizeof(T)), "cg session has the wrong real_type");                                                                      \
             *count = static_cast<cg_session<T> *>(cg->ranks[0].get())->get_trace(out, capacity);                                                                                 \
         });                                                                                                                                                                      \
     }                                                                                                                                                                            \
     int plssvm_b200_cg_finish_##SUF(plssvm_b200_cg *cg, T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                       \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(cg != nullptr && !cg->ranks.empty(), "cg session is NULL");                                                                                               \
-            std::unique_ptr<plssvm_b200_cg> owner(cg); /* the session is released on every path */                                                                               \
+            PB_REQUIRE(handle_live(cg) && !cg->ranks.empty(), "cg session is NULL or has been finished / aborted / destroyed with its context");                                 \
+            struct releaser {                                                                                                                                                    \
+                plssvm_b200_cg *h;                                                                                                                                               \
+                ~releaser() { cg_release(h); } /* the session is released on every path */                                                                                       \
+            } guard{ cg };                                                                                                                                                       \
             PB_REQUIRE(cg->elem_size == static_cast<int>(sizeof(T)), "cg session has the wrong real_type");                                                                      \
             PB_REQUIRE(alpha_out != nullptr && rho_out != nullptr, "alpha_out and rho_out must not be NULL");                                                                    \
             for_each_rank(cg->ctx, [&](plssvm_b200_ctx *, const int g) {                                                                                                         \
                 static_cast<cg_session<T> *>(cg->ranks[g].get())->finish(alpha_out, rho_out, iters_out, residual_out, g == 0);                                                   \
-                cg->ranks[g].reset();                                                                                                                                            \
             });                                                                                                                                                                  \
         });                                                                                                                                                                      \
     }                                                                                                                                                                            \
     int plssvm_b200_solve_dataset_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps, uint64_t max_iter,   \
                                         T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                                       \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");                                                                                                                       \
             const host_timer ht;                                                                                                                                                 \
             for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                  \
             solve_dataset<T>(ctx, X, y, kernel, degree, gamma, coef0, cost, eps, max_iter, alpha_out, rho_out, iters_out, residual_out);                                         \
@@ -1689,7 +1738,7 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     }                                                                                                                                                                            \
     static void solve_host_##SUF(plssvm_b200_ctx *ctx, const host_matrix<T> &X, size_t N, size_t d, const T *y, int kernel, int degree, T gamma, T coef0, T cost, T eps,        \
                                  uint64_t max_iter, T *alpha_out, T *rho_out, uint64_t *iters_out, T *residual_out) {                                                            \
-        PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                           \
+        PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");                                                                                                                           \
         PB_REQUIRE(X.valid(), "The data must not be empty!");                                                                                                                    \
         const host_timer ht;                                                                                                                                                     \
         for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                      \
@@ -1718,7 +1767,7 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     int plssvm_b200_predict_dataset_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, T rho, T *w_inout, int *w_valid, plssvm_b200_dataset *points,          \
                                           int kernel, int degree, T gamma, T coef0, T *out) {                                                                                   \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr && points != nullptr, "context or points is NULL");                                                                                        \
+            PB_REQUIRE(handle_live(ctx) && handle_live(points), "context or points data set is NULL or has been destroyed");                                                                                        \
             const host_timer ht;                                                                                                                                                 \
             for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                  \
             predict_common<T>(ctx, SV, alpha, rho, w_inout, w_valid, points, host_matrix<T>{}, points->N, kernel, degree, gamma, coef0, out, true);                              \
@@ -1727,7 +1776,7 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     }                                                                                                                                                                            \
     static void predict_host_##SUF(plssvm_b200_ctx *ctx, const host_matrix<T> &SV, size_t n_sv, size_t d, const T *alpha, T rho, T *w_inout, int *w_valid,                      \
                                    const host_matrix<T> &points, size_t m, int kernel, int degree, T gamma, T coef0, T *out) {                                                   \
-        PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                           \
+        PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");                                                                                                                           \
         PB_REQUIRE(points.valid(), "The data points to predict must not be empty!");                                                                                             \
         const host_timer ht;                                                                                                                                                     \
         for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                      \
@@ -1757,7 +1806,7 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     }                                                                                                                                                                            \
     int plssvm_b200_q_kernel_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, int kernel, int degree, T gamma, T coef0, T *q_out, T *k_last) {                               \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");                                                                                                                       \
             reset_timings(ctx);                                                                                                                                                  \
             api_q_kernel<T>(ctx, X, kernel, degree, gamma, coef0, q_out, k_last);                                                                                                \
         });                                                                                                                                                                      \
@@ -1765,14 +1814,14 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     int plssvm_b200_matvec_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *X, const T *q, const T *v, T QA_cost, T cost_inv, T add, int kernel, int degree, T gamma, T coef0,  \
                                  T *ret_inout) {                                                                                                                                 \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");                                                                                                                       \
             for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                  \
             api_matvec<T>(ctx, X, q, v, QA_cost, cost_inv, add, kernel, degree, gamma, coef0, ret_inout);                                                                        \
         });                                                                                                                                                                      \
     }                                                                                                                                                                            \
     int plssvm_b200_w_kernel_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, T *w_out) {                                                                   \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr, "context is NULL");                                                                                                                       \
+            PB_REQUIRE(handle_live(ctx), "context is NULL or has been destroyed");                                                                                                                       \
             reset_timings(ctx);                                                                                                                                                  \
             api_w_kernel<T>(ctx, SV, alpha, w_out);                                                                                                                              \
         });                                                                                                                                                                      \
@@ -1780,7 +1829,7 @@ int plssvm_b200_cg_abort(plssvm_b200_cg *cg) {
     int plssvm_b200_predict_kernel_##SUF(plssvm_b200_ctx *ctx, plssvm_b200_dataset *SV, const T *alpha, plssvm_b200_dataset *points, int kernel, int degree, T gamma, T coef0,  \
                                          T *out) {                                                                                                                               \
         return guarded([&] {                                                                                                                                                     \
-            PB_REQUIRE(ctx != nullptr && points != nullptr, "context or points is NULL");                                                                                        \
+            PB_REQUIRE(handle_live(ctx) && handle_live(points), "context or points data set is NULL or has been destroyed");                                                                                        \
             PB_REQUIRE(kernel != PLSSVM_B200_KERNEL_LINEAR, "run_predict_kernel is only defined for the polynomial and rbf kernels (linear uses run_w_kernel)");                 \
             for_all_members(ctx, [](plssvm_b200_ctx *c) { reset_timings(c); });                                                                                                  \
             predict_common<T>(ctx, SV, alpha, T(0), nullptr, nullptr, points, host_matrix<T>{}, points->N, kernel, degree, gamma, coef0, out, false);                            \

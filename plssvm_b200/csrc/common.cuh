@@ -54,6 +54,7 @@ struct TileParams {
     KernelParams<T> kp;
     T *partial;            // [T_rows][T_cols][TILE] (SYM: [T][T][TILE], slot (A, B) = contribution of block B to output block A)
     const int *done;       // CG convergence flag: all kernels of a speculatively enqueued iteration exit when set
+    int slow_drain;        // debugging / A-B measurements: 1 = the fp32 int8-slice epilogue converts before it releases TMEM (option "fp32_fast_drain" = 0)
 };
 
 // integer power by repeated squaring; matches std::pow(x, (real) degree) of kernel_function_types.hpp:86-89 to a few ulp

@@ -127,10 +127,16 @@ struct event_pair_timer {
         PB_CUDA(cudaEventRecord(ev[used + 1], s));
         used += 2;
     }
-    // sums the pairs recorded since the last call (the stream must have been synchronised past them) and recycles their events
+    // sums the pairs that have completed since the last call (pairs still in flight are left for the next call) and recycles their events
     double collect() {
         double t = 0.0;
         for (; read + 1 < used; read += 2) {
+            const cudaError_t q = cudaEventQuery(ev[read + 1]);
+            if (q == cudaErrorNotReady) {
+                (void) cudaGetLastError();
+                break;
+            }
+            PB_CUDA(q);
             float ms = 0.f;
             PB_CUDA(cudaEventElapsedTime(&ms, ev[read], ev[read + 1]));
             t += ms;
@@ -170,12 +176,15 @@ struct plssvm_b200_ctx {
     int linear_factorized = 0;   // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     int balance = 1;             // several ranks: re-cut the tile shares from the measured tile-kernel rates every `balance_interval` iterations
     int balance_interval = 8;
+    int fp32_fast_drain = 1;     // fp32 int8-slice epilogue: release TMEM before the fp64 -> fp32 conversion (0: the round-1 order, for A/B measurements)
     int virtual_skew = 0;        // testing aid (virtual ranks): percent by which the tile shares grow from the first to the last rank
     int shard_upload = 1;        // several ranks: every rank uploads 1 / world of the rows over its own PCIe link, ncclAllGather over NVLink
     // timings of the last call (accumulated over the lifetime of an open CG session)
     plssvm_b200_timings tm{};
     pbrt::event_pair_timer tile_timer, matvec_timer;
     int open_sessions = 0;
+    std::vector<plssvm_b200_dataset *> live_datasets;  // (leader) data sets and CG sessions created from this context: destroyed with it
+    std::vector<struct plssvm_b200_cg *> live_sessions;
     std::vector<double> last_trace;  // residual history r.r of the last finished solve (entry k: after k iterations)
     cudaEvent_t ev_loop0 = nullptr, ev_loop1 = nullptr;
     PFN_cuTensorMapEncodeTiled_v12000 encode_tiled = nullptr;

@@ -202,6 +202,18 @@ __device__ __forceinline__ void tmem_ld_32x32b_x8(const std::uint32_t taddr, std
                  : "r"(taddr)
                  : "memory");
 }
+// 32 columns of this thread's TMEM lane, no wait (several loads are put in flight before one tcgen05.wait::ld)
+__device__ __forceinline__ void tmem_ld_32x32b_x32_nowait(const std::uint32_t taddr, std::uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+          "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // exact int32 -> fp64 on the FP64 add pipe: (2^52 + 2^31 + a) - (2^52 + 2^31)
 __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __hiloint2double(0x43300000, static_cast<int>(a ^ 0x80000000u)) - 4503601774854144.0; }
@@ -413,9 +425,9 @@ tile_kernel_i8(const TileParams<T> p) {
                 }
                 named_bar_sync(1, I8_EPI_THREADS);
                 const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row];
-                // fp32, S = 3, d <= 1984: the two upper diagonals fit one int32 (|ACC_2| 2^8 + |ACC_1| <= d (2^20 + 2^14) < 2^31), so the recombination
-                // costs one IMAD + 3 instead of 5 fp64 operations per element (the fp64 pipe, 64 / clk / SM, paces the TMEM drain of the fp32 kernel);
-                // the sum is 256 x the value, folded into the row scale.  Both forms are exact in fp64: bit-identical results.
+                // fp32, S = 3, d <= 1984: the two upper diagonals fit one int32 (|ACC_2| 2^8 + |ACC_1| <= d (2^20 + 2^14) < 2^31), so an element is two
+                // words (fast drain below) and its recombination one IMAD + 3 instead of 5 fp64 operations; the sum is 256 x the value, folded
+                // into the row scale.  Both forms are exact in fp64: bit-identical results.
                 const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;
                 const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
 
@@ -426,19 +438,43 @@ tile_kernel_i8(const TileParams<T> p) {
                 // phase 1: S int32 diagonals -> one value per element (Horner in fp64 from the least significant diagonal: every step exact
                 // up to one rounding relative to the running sum)
                 T a[CPT];
-                #pragma unroll
-                for (int g = 0; g < CPT / 8; ++g) {
-                    std::uint32_t r[S][8];
-                    #pragma unroll
-                    for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
-                    tmem_ld_wait();
-                    if (fold3) {
+                bool released = false;
+                if constexpr (sizeof(T) == 4 && S == 3 && CPT == 64) {
+                    if (fold3 && p.slow_drain == 0) {
+                        // fp32 fast drain (measured with tools/tmem_probe: the fp64 -> fp32 conversion runs at ~12 elements / clk / SM and a
+                        // tcgen05.ld + wait round trip costs a few hundred cycles, so converting while the accumulators are still held kept the
+                        // tensor pipe idle for ~1/3 of a d = 1024 unit).  Here the raw int32 diagonals of all 64 columns are pulled into
+                        // registers with two rounds of three 32-column loads, folded to two words per element by integer arithmetic, and TMEM
+                        // goes back to the MMA warp BEFORE any floating-point work; the conversion overlaps the next unit's MMAs.
+                        std::uint32_t hi[CPT], lo[CPT];
                         #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const std::uint32_t hi = r[S - 1][j] * 256u + r[S >= 2 ? S - 2 : 0][j];
-                            a[g * 8 + j] = static_cast<T>(fma(i32_to_f64(r[0][j]), 0.00390625, i32_to_f64(hi)));
+                        for (int half = 0; half < 2; ++half) {
+                            std::uint32_t r0[32], r1[32], r2[32];
+                            tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(0 * NH + half * 32), r0);
+                            tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(1 * NH + half * 32), r1);
+                            tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(2 * NH + half * 32), r2);
+                            tmem_ld_wait();
+                            #pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                hi[half * 32 + j] = r2[j] * 256u + r1[j];
+                                lo[half * 32 + j] = r0[j];
+                            }
                         }
-                    } else {
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive(tempty); }
+                        released = true;
+                        #pragma unroll
+                        for (int j = 0; j < CPT; ++j) { a[j] = static_cast<T>(fma(i32_to_f64(lo[j]), 0.00390625, i32_to_f64(hi[j]))); }
+                    }
+                }
+                if (!released) {
+                    #pragma unroll
+                    for (int g = 0; g < CPT / 8; ++g) {
+                        std::uint32_t r[S][8];
+                        #pragma unroll
+                        for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
+                        tmem_ld_wait();
                         #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             double s = i32_to_f64(r[0][j]);
@@ -447,11 +483,11 @@ tile_kernel_i8(const TileParams<T> p) {
                             a[g * 8 + j] = static_cast<T>(s);
                         }
                     }
+                    // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(tempty); }
                 }
-                // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(tempty); }
 
                 // phase 2: kernel function and the weighted sums
                 #pragma unroll

@@ -55,12 +55,12 @@ def test_errors_against_the_exact_target(be, case, golden_dir):
             be.set_option("ignore_convergence", 0)
             assert r["iterations"] == k
             row["alpha_err_k"], row["rho_err_k"] = check_solution_vs_exact(r["alpha"], r["rho"], e[f"{name}/alpha_k"], e[f"{name}/rho_k"], e[f"{name}/ref_alpha_err_k"],
-                                                                           e[f"{name}/ref_rho_err_k"], X.dtype, f"{name}/impl{impl}/k={k}")
+                                                                           e[f"{name}/ref_rho_err_k"], X.dtype, float(g[f"{name}/QA_cost"]), f"{name}/impl{impl}/k={k}")
             # the solve as a user runs it (stopping rule active) against the converged solution of the reduced system
             r = be.solve(ds, y, kernel, eps=c["eps"], max_iter=c["max_iter"], cost=c["cost"], **pr)
             row["iterations"] = r["iterations"]
             row["alpha_err_star"], row["rho_err_star"] = check_solution_vs_exact(r["alpha"], r["rho"], e[f"{name}/alpha_star"], e[f"{name}/rho_star"], e[f"{name}/ref_alpha_err_star"],
-                                                                                 e[f"{name}/ref_rho_err_star"], X.dtype, f"{name}/impl{impl}/star")
+                                                                                 e[f"{name}/ref_rho_err_star"], X.dtype, float(g[f"{name}/QA_cost"]), f"{name}/impl{impl}/star")
             # decision values of the golden model
             vals, _ = be.predict_values(X, g[f"{name}/alpha"], float(g[f"{name}/rho"]), c["P"], kernel, **pr)
             row["predict_err"] = check_single_vs_exact(vals, e[f"{name}/predict"], e[f"{name}/ref_predict_err"], X.dtype, f"{name}/impl{impl}/predict")
