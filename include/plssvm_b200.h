@@ -66,6 +66,12 @@ typedef struct plssvm_b200_timings {
     double cg_avg_iteration_ms; /* host wall time of the iteration loop / iterations (what the reference's avg_iteration_time measures) */
     uint64_t rebalances;        /* several ranks: how often the tile shares were re-cut from the measured tile-kernel rates */
     uint64_t fallback_batches;  /* predict: host-staged batches that were re-run with the floating-point tensor tiles because of badly scaled rows */
+    /* option "tile_stats" = 1 (int8-slice tiles only; synchronises after every tile launch): where the warp-specialised roles of the LAST tile
+     * launch spent their time, as fractions of the MMA warp's loop, averaged over the CTAs */
+    double tile_mma_wait_operands; /* MMA warp waiting for a ring stage to be filled by the TMA producer */
+    double tile_mma_wait_drain;    /* MMA warp waiting for the epilogue to hand the TMEM accumulators back */
+    double tile_producer_wait;     /* producer waiting for a free ring stage (= operands arrive faster than they are consumed) */
+    double tile_epilogue_wait;     /* epilogue waiting for the accumulators of the next unit */
 } plssvm_b200_timings;
 
 /* ---- context ----------------------------------------------------------------------------------------------------
@@ -95,6 +101,8 @@ const char *plssvm_b200_last_error(void);
  * re-cut the tile shares every "balance_interval" (default 8) iterations in proportion to the tile-kernel rates the ranks
  * measured — GPUs under a power cap do not run at the same clock; 0 = fixed equal shares, bit-reproducible run to run),
  * "shard_upload" (0/1, default 1; several devices / ranks: each uploads 1 / world of the rows, NCCL all-gather);
+ * "tile_stats" (0/1, profiling: per-role wait-cycle counters of the int8-slice tile kernel, see plssvm_b200_timings), "fp32_fast_drain" (0/1,
+ * default 1; A/B switch of the fp32 epilogue: release TMEM before / after the fp64 -> fp32 conversion, bit-identical results);
  * testing aid on ONE device: "virtual_world" = G, "virtual_rank" = g make the context compute rank g's share of a G-rank run without
  * a communicator — the matvec returns the partial result of rank g's tiles (the G partial results add up to the full product),
  * predict writes only rank g's range of points; "virtual_skew" = p makes the tile shares unequal (+- p / 2 percent) */

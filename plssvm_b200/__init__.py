@@ -49,7 +49,8 @@ class Timings(ctypes.Structure):
                 ("matvec_calls", ctypes.c_uint64), ("kernel_launches", ctypes.c_uint64), ("matvec_flops", ctypes.c_double), ("h2d_bytes", ctypes.c_double),
                 ("d2h_bytes", ctypes.c_double), ("impl_used", ctypes.c_int), ("n_devices", ctypes.c_int),
                 ("cg_iterations", ctypes.c_uint64), ("cg_max_iterations", ctypes.c_uint64), ("cg_residuum", ctypes.c_double), ("cg_target_residuum", ctypes.c_double),
-                ("cg_epsilon", ctypes.c_double), ("cg_avg_iteration_ms", ctypes.c_double), ("rebalances", ctypes.c_uint64), ("fallback_batches", ctypes.c_uint64)]
+                ("cg_epsilon", ctypes.c_double), ("cg_avg_iteration_ms", ctypes.c_double), ("rebalances", ctypes.c_uint64), ("fallback_batches", ctypes.c_uint64),
+                ("tile_mma_wait_operands", ctypes.c_double), ("tile_mma_wait_drain", ctypes.c_double), ("tile_producer_wait", ctypes.c_double), ("tile_epilogue_wait", ctypes.c_double)]
 
     def as_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

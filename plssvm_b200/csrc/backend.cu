@@ -422,10 +422,35 @@ void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p_in, const int imp
     ctx->tm.impl_used = impl;
     TileParams<T> p = p_in;
     p.slow_drain = ctx->fp32_fast_drain != 0 ? 0 : 1;
+    const bool stats = ctx->tile_stats != 0 && (impl == 6 || impl == 7);
+    const std::size_t stat_words = static_cast<std::size_t>(ctx->num_sms) * 8;
+    if (stats) {
+        p.stats = workspace<unsigned long long>(ctx, plssvm_b200_ctx::WS_STATS, stat_words);
+        PB_CUDA(cudaMemsetAsync(p.stats, 0, stat_words * sizeof(unsigned long long), ctx->stream));
+    }
     switch (p.kp.kernel) {
         case pb::K_LINEAR: launch_tiles_t<T, pb::K_LINEAR, MODE>(ctx, p, impl); break;
         case pb::K_POLYNOMIAL: launch_tiles_t<T, pb::K_POLYNOMIAL, MODE>(ctx, p, impl); break;
         default: launch_tiles_t<T, pb::K_RBF, MODE>(ctx, p, impl); break;
+    }
+    if (stats) {  // profiling only: read the per-CTA role counters of this launch
+        std::vector<unsigned long long> h(stat_words);
+        PB_CUDA(cudaMemcpyAsync(h.data(), p.stats, stat_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
+        double f[4] = { 0, 0, 0, 0 };
+        int ctas = 0;
+        for (int b = 0; b < ctx->num_sms; ++b) {
+            const double total = static_cast<double>(h[b * 8]);
+            if (total <= 0.0) { continue; }
+            ++ctas;
+            for (int k = 0; k < 4; ++k) { f[k] += static_cast<double>(h[b * 8 + 1 + k]) / total; }
+        }
+        if (ctas > 0) {
+            ctx->tm.tile_mma_wait_operands = f[0] / ctas;
+            ctx->tm.tile_mma_wait_drain = f[1] / ctas;
+            ctx->tm.tile_producer_wait = f[2] / ctas;
+            ctx->tm.tile_epilogue_wait = f[3] / ctas;
+        }
     }
 }
 
@@ -1477,6 +1502,15 @@ int plssvm_b200_create(const int *device_ids, int n_dev, plssvm_b200_ctx **out) 
                     members[g]->tm.n_devices = static_cast<int>(members.size());
                 }
                 members[0]->members = members;
+                // NCCL connects its channels lazily, at the first collective (hundreds of milliseconds): do that here, like the device
+                // initialisation of the reference's constructor (csvm.cu:48-86), not inside the first fit / predict call
+                for_each_rank(members[0], [&](plssvm_b200_ctx *c, const int) {
+                    double *buf = workspace<double>(c, plssvm_b200_ctx::WS_MISC, 64);
+                    PB_CUDA(cudaMemsetAsync(buf, 0, 64 * sizeof(double), c->stream));
+                    all_reduce_sum(c, buf, 16);
+                    nccl.check(nccl.AllGather(buf + c->rank, buf, 1, NCCL_FLOAT64, c->comm, c->stream), "ncclAllGather");
+                    PB_CUDA(cudaStreamSynchronize(c->stream));
+                });
             }
         } catch (...) {
             for (auto *m : members) { destroy_device_context(m); }
@@ -1541,7 +1575,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 ctx->virtual_skew = static_cast<int>(value);
             }
             return;
-        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain") {
+        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain" && k != "tile_stats") {
             throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
         }
         for_all_members(ctx, [&](plssvm_b200_ctx *c) {
@@ -1565,6 +1599,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 c->shard_upload = value != 0;
             } else if (k == "fp32_fast_drain") {
                 c->fp32_fast_drain = value != 0;
+            } else if (k == "tile_stats") {
+                c->tile_stats = value != 0;
             }
         });
     });
@@ -1627,6 +1663,11 @@ int plssvm_b200_comm_init(plssvm_b200_ctx *ctx, int rank, int world_size, const 
         ctx->rank = rank;
         ctx->world = world_size;
         ctx->tm.n_devices = world_size;
+        double *buf = workspace<double>(ctx, plssvm_b200_ctx::WS_MISC, 64);  // first collectives: NCCL connects its channels here, not inside the first solve
+        PB_CUDA(cudaMemsetAsync(buf, 0, 64 * sizeof(double), ctx->stream));
+        all_reduce_sum(ctx, buf, 16);
+        nccl.check(nccl.AllGather(buf + rank, buf, 1, NCCL_FLOAT64, ctx->comm, ctx->stream), "ncclAllGather");
+        PB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
 

@@ -54,6 +54,7 @@ struct TileParams {
     KernelParams<T> kp;
     T *partial;            // [T_rows][T_cols][TILE] (SYM: [T][T][TILE], slot (A, B) = contribution of block B to output block A)
     const int *done;       // CG convergence flag: all kernels of a speculatively enqueued iteration exit when set
+    unsigned long long *stats;  // optional (option "tile_stats"): per CTA 8 words of cycle counters of the int8-slice kernel's roles (tile_i8.cuh)
     int slow_drain;        // debugging / A-B measurements: 1 = the fp32 int8-slice epilogue converts before it releases TMEM (option "fp32_fast_drain" = 0)
 };
 
@@ -77,15 +78,33 @@ __device__ __forceinline__ double pb_exp(const double x) { return exp(x); }
 __device__ __forceinline__ float pb_fma(const float a, const float b, const float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double pb_fma(const double a, const double b, const double c) { return fma(a, b, c); }
 
+// the same with the degree known at compile time (DEG = 0: the runtime value); identical operation order, hence identical rounding:
+// the loop above yields x, x x, x (x x), (x x) (x x) for degree 1 .. 4
+template <int DEG, typename T>
+__device__ __forceinline__ T ipow_ct(const T x, const int degree) {
+    if constexpr (DEG == 1) {
+        return x;
+    } else if constexpr (DEG == 2) {
+        return x * x;
+    } else if constexpr (DEG == 3) {
+        return x * (x * x);
+    } else if constexpr (DEG == 4) {
+        const T sq = x * x;
+        return sq * sq;
+    } else {
+        return ipow(x, degree);
+    }
+}
+
 // kernel function from the contraction result: `dot` = x_i . x_j, sq_* = squared norms (rbf only)
 // (kernel_function_types.hpp:75-97; rbf through |x_i|^2 + |x_j|^2 - 2 x_i.x_j instead of the reference's direct
 //  sum of squared differences, clamped at 0 — see DESIGN.md "numerics")
-template <int KERNEL, typename T>
+template <int KERNEL, typename T, int DEG = 0>
 __device__ __forceinline__ T kernel_from_dot(const T dot, const T sq_i, const T sq_j, const KernelParams<T> &kp) {
     if constexpr (KERNEL == K_LINEAR) {
         return dot;
     } else if constexpr (KERNEL == K_POLYNOMIAL) {
-        return ipow(pb_fma(kp.gamma, dot, kp.coef0), kp.degree);
+        return ipow_ct<DEG>(pb_fma(kp.gamma, dot, kp.coef0), kp.degree);
     } else {
         T d2 = pb_fma(T(-2), dot, sq_i + sq_j);
         d2 = d2 < T(0) ? T(0) : d2;  // (a NaN distance stays NaN)

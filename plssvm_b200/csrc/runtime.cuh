@@ -176,6 +176,7 @@ struct plssvm_b200_ctx {
     int linear_factorized = 0;   // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     int balance = 1;             // several ranks: re-cut the tile shares from the measured tile-kernel rates every `balance_interval` iterations
     int balance_interval = 8;
+    int tile_stats = 0;          // profiling: per-role wait-cycle counters of the int8-slice tile kernel (synchronises after every tile launch)
     int fp32_fast_drain = 1;     // fp32 int8-slice epilogue: release TMEM before the fp64 -> fp32 conversion (0: the round-1 order, for A/B measurements)
     int virtual_skew = 0;        // testing aid (virtual ranks): percent by which the tile shares grow from the first to the last rank
     int shard_upload = 1;        // several ranks: every rank uploads 1 / world of the rows over its own PCIe link, ncclAllGather over NVLink
@@ -197,7 +198,7 @@ struct plssvm_b200_ctx {
     void *ring[2] = { nullptr, nullptr };
     cudaEvent_t ev_ring[2] = { nullptr, nullptr };
     // grow-only device workspaces kept across calls
-    enum ws_slot { WS_PARTIAL = 0, WS_OUT, WS_ALPHA, WS_W, WS_STAGE0, WS_STAGE1, WS_SQ0, WS_SQ1, WS_HI0, WS_HI1, WS_LO0, WS_LO1, WS_I8_0, WS_I8_1, WS_SC0, WS_SC1, WS_MISC, WS_COUNT };
+    enum ws_slot { WS_PARTIAL = 0, WS_OUT, WS_ALPHA, WS_W, WS_STAGE0, WS_STAGE1, WS_SQ0, WS_SQ1, WS_HI0, WS_HI1, WS_LO0, WS_LO1, WS_I8_0, WS_I8_1, WS_SC0, WS_SC1, WS_MISC, WS_STATS, WS_COUNT };
     void *ws_ptr[WS_COUNT] = {};
     std::size_t ws_bytes[WS_COUNT] = {};
     // caching allocator: blocks released by RAII buffers are kept for the next call (cudaMalloc / cudaFree of multi-GB buffers cost

@@ -32,6 +32,8 @@
 #pragma once
 
 #include "common.cuh"
+
+#include <type_traits>
 #include "tile_dmma.cuh"  // mbarrier / TMA helpers
 #include "tile_tf32.cuh"  // tcgen05 helpers
 #include "tile_tf32_2sm.cuh"  // cluster helpers
@@ -224,7 +226,7 @@ __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __h
 // TMA multicasts it to its mate — half the L2 -> SM traffic per CTA (the single-CTA kernel runs at 92 % of the L2 throughput cap).  A stage is
 // refilled once the MMA warps of all three CTAs that write into or read from it have released it (multicast tcgen05.commit, count 3).
 template <typename T, int S_, int KERNEL, int MODE, int CL>
-__global__ void __launch_bounds__(I8_THREADS, 1)
+__global__ void __launch_bounds__(I8_THREADS, 1)  // (10 warps = 3 on one SM sub-partition: 170 registers per thread at most)
 tile_kernel_i8(const TileParams<T> p) {
     using L8 = I8Layout<T, S_>;
     static_assert(CL == 1 || CL == 4, "cluster size");
@@ -297,6 +299,7 @@ tile_kernel_i8(const TileParams<T> p) {
         // ===== TMA producer =====
         if (lane == 0) {
             std::uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;  // cycles spent waiting for a free ring stage (p.stats)
             const std::uint16_t mask_a = static_cast<std::uint16_t>(3u << (2 * cr));                // the two CTAs of this cluster row
             const std::uint16_t mask_b = static_cast<std::uint16_t>((1u << cc) | (1u << (2 + cc)));  // the two CTAs of this cluster column
             for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
@@ -310,7 +313,9 @@ tile_kernel_i8(const TileParams<T> p) {
                     const std::int8_t *src_a = p.A_i8 + static_cast<std::size_t>(Il) * num_slabs * L8::A_BYTES;
                     const std::int8_t *src_b = p.B_i8 + static_cast<std::size_t>(Jl) * num_slabs * L8::A_BYTES + h * L8::B_SLICE;
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
+                        const long long c0 = p.stats != nullptr ? clock64() : 0;
                         mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                        if (p.stats != nullptr) { w_empty += clock64() - c0; }
                         const std::uint32_t dst = smem_u32(stages + stage * L8::STAGE_BYTES);
                         const std::uint32_t bar = full0 + 8 * stage;
                         mbar_arrive_expect_tx(bar, L8::STAGE_BYTES);
@@ -341,19 +346,26 @@ tile_kernel_i8(const TileParams<T> p) {
                     }
                 }
             }
+            if (p.stats != nullptr) { p.stats[blockIdx.x * 8 + 3] = static_cast<unsigned long long>(w_empty); }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             std::uint32_t stage = 0, phase = 0, unit_iter = 0;
+            long long w_full = 0, w_tempty = 0;  // cycles waiting for operands / for the epilogue to hand the accumulators back (p.stats)
+            const long long c_begin = p.stats != nullptr ? clock64() : 0;
             const std::uint16_t mask_rel = static_cast<std::uint16_t>((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));  // this CTA, its row mate, its column mate
             for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
                 for (int h = 0; h < UNITS; ++h, ++unit_iter) {
+                    const long long c0 = p.stats != nullptr ? clock64() : 0;
                     mbar_wait(tempty, (unit_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous unit
+                    if (p.stats != nullptr) { w_tempty += clock64() - c0; }
                     tcgen05_fence_after();
                     for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
+                        const long long c1 = p.stats != nullptr ? clock64() : 0;
                         mbar_wait(full0 + 8 * stage, phase);
+                        if (p.stats != nullptr) { w_full += clock64() - c1; }
                         tcgen05_fence_after();
                         const std::uint32_t base = smem_u32(stages + stage * L8::STAGE_BYTES);
                         const std::uint64_t d_a = umma_desc_sw64(base), d_b = umma_desc_sw64(base + L8::A_BYTES);
@@ -387,6 +399,11 @@ tile_kernel_i8(const TileParams<T> p) {
                     }
                     umma_commit(tfull);  // all S accumulators of this unit complete
                 }
+            }
+            if (p.stats != nullptr) {
+                p.stats[blockIdx.x * 8 + 0] = static_cast<unsigned long long>(clock64() - c_begin);
+                p.stats[blockIdx.x * 8 + 1] = static_cast<unsigned long long>(w_full);
+                p.stats[blockIdx.x * 8 + 2] = static_cast<unsigned long long>(w_tempty);
             }
         }
         __syncwarp();
@@ -431,7 +448,9 @@ tile_kernel_i8(const TileParams<T> p) {
                 const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;
                 const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
 
+                const long long c2 = (p.stats != nullptr && tid == 64) ? clock64() : 0;
                 mbar_wait(tfull, unit_iter & 1u);
+                if (p.stats != nullptr && tid == 64) { atomicAdd(p.stats + blockIdx.x * 8 + 4, static_cast<unsigned long long>(clock64() - c2)); }
                 tcgen05_fence_after();
                 const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * CPT);
 
@@ -489,19 +508,57 @@ tile_kernel_i8(const TileParams<T> p) {
                     if (lane == 0) { mbar_arrive(tempty); }
                 }
 
-                // phase 2: kernel function and the weighted sums
-                #pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    const int cl = ch * CPT + j;
-                    const T dot = a[j] * (sci * s_col[3 * NH + cl]);
-                    const T kv = kernel_from_dot<KERNEL>(dot, sqi, s_col[2 * NH + cl], p.kp);
-                    T t = kv;
-                    if constexpr (MODE == MODE_SYM) {
-                        t = kv + qa - qi - s_col[0 * NH + cl];
-                        if (diag && row == h * NH + cl) { t += p.cost_inv; }
+                // phase 2: kernel function and the weighted sums.  The loop is instantiated per (polynomial degree, diagonal tile) so that the power
+                // is straight-line code and off-diagonal tiles carry no diagonal test (at d = 1024 the fp32 epilogue, not the tensor pipe, paces
+                // the kernel: profiles/r02/tile_role_stats.jsonl); the column vectors come out of shared memory as 16-byte vectors.  Operation
+                // order and rounding are unchanged.
+                auto phase2 = [&](auto deg_tag, auto diag_tag) {
+                    constexpr int DEG = decltype(deg_tag)::value;
+                    constexpr bool DIAG = decltype(diag_tag)::value;
+                    constexpr int V = 16 / static_cast<int>(sizeof(T));  // elements per 16-byte shared-memory load
+                    struct alignas(16) vec {
+                        T x[V];
+                    };
+                    #pragma unroll
+                    for (int j0 = 0; j0 < CPT; j0 += V) {
+                        const int c0 = ch * CPT + j0;
+                        const vec scj = *reinterpret_cast<const vec *>(s_col + 3 * NH + c0);
+                        const vec vj = *reinterpret_cast<const vec *>(s_col + 1 * NH + c0);
+                        vec sqj{}, qj{};
+                        if constexpr (KERNEL == K_RBF) { sqj = *reinterpret_cast<const vec *>(s_col + 2 * NH + c0); }
+                        if constexpr (MODE == MODE_SYM) { qj = *reinterpret_cast<const vec *>(s_col + 0 * NH + c0); }
+                        #pragma unroll
+                        for (int u = 0; u < V; ++u) {
+                            const int j = j0 + u;
+                            const T dot = a[j] * (sci * scj.x[u]);
+                            const T kv = kernel_from_dot<KERNEL, T, DEG>(dot, sqi, sqj.x[u], p.kp);
+                            T t = kv;
+                            if constexpr (MODE == MODE_SYM) {
+                                t = kv + qa - qi - qj.x[u];
+                                if constexpr (DIAG) {
+                                    if (row == h * NH + c0 + u) { t += p.cost_inv; }
+                                }
+                            }
+                            rowacc = pb_fma(t, vj.x[u], rowacc);
+                            a[j] = t * vi;  // mirrored contribution of this row to column c0 + u
+                        }
                     }
-                    rowacc = pb_fma(t, s_col[1 * NH + cl], rowacc);
-                    a[j] = t * vi;  // mirrored contribution of this row to column cl
+                };
+                auto phase2_deg = [&](auto deg_tag) {
+                    if (diag) {
+                        phase2(deg_tag, std::true_type{});
+                    } else {
+                        phase2(deg_tag, std::false_type{});
+                    }
+                };
+                if constexpr (KERNEL == K_POLYNOMIAL) {
+                    switch (p.kp.degree) {  // CTA-uniform
+                        case 2: phase2_deg(std::integral_constant<int, 2>{}); break;
+                        case 3: phase2_deg(std::integral_constant<int, 3>{}); break;
+                        default: phase2_deg(std::integral_constant<int, 0>{}); break;
+                    }
+                } else {
+                    phase2_deg(std::integral_constant<int, 0>{});
                 }
                 if constexpr (MODE == MODE_SYM) {
                     if (!diag) {  // CTA-uniform
