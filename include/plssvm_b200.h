@@ -102,7 +102,9 @@ const char *plssvm_b200_last_error(void);
  * measured — GPUs under a power cap do not run at the same clock; 0 = fixed equal shares, bit-reproducible run to run),
  * "shard_upload" (0/1, default 1; several devices / ranks: each uploads 1 / world of the rows, NCCL all-gather);
  * "tile_stats" (0/1, profiling: per-role wait-cycle counters of the int8-slice tile kernel, see plssvm_b200_timings), "fp32_fast_drain" (0/1,
- * default 1; A/B switch of the fp32 epilogue: release TMEM before / after the fp64 -> fp32 conversion, bit-identical results);
+ * default 1; A/B switch of the fp32 epilogue: release TMEM before / after the fp64 -> fp32 conversion, bit-identical results),
+ * "i8_a_via_tmem" (0/1, default 0; fp64 int8-slice tiles: the A digit planes that feed two MMAs per step are staged in tensor memory with tcgen05.cp
+ * and read by TS-form MMAs — bit-identical, measured 4 % slower, kept as an experiment);
  * testing aid on ONE device: "virtual_world" = G, "virtual_rank" = g make the context compute rank g's share of a G-rank run without
  * a communicator — the matvec returns the partial result of rank g's tiles (the G partial results add up to the full product),
  * predict writes only rank g's range of points; "virtual_skew" = p makes the tile shares unequal (+- p / 2 percent) */

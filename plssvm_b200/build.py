@@ -7,7 +7,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libplssvm_b200.so")
+LIB = os.environ.get("PLSSVM_B200_LIB") or os.path.join(HERE, "libplssvm_b200.so")  # (the override is for A/B measurements of two builds)
 SOURCES = ["backend.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))) + [os.path.join("..", "..", "include", "plssvm_b200.h")]
 NVCC_FLAGS = [
@@ -36,6 +36,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     experimental = ["-DPLSSVM_B200_EXPERIMENTAL"] if os.environ.get("PLSSVM_B200_EXPERIMENTAL", "0") not in ("", "0") else []
+    experimental += os.environ.get("PLSSVM_B200_DEFINES", "").split()  # extra -D flags (A/B builds)
     cmd = [_nvcc(), *NVCC_FLAGS, *experimental, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     env = dict(os.environ)
     env.pop("CXX", None)  # the image's CXX points at a compiler wrapper without OpenMP specs; nvcc should use the distro g++

@@ -314,6 +314,9 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
             constexpr int S = decltype(slices)::value, CL = decltype(cluster)::value;
             using L8 = pb::I8Layout<T, S>;
             auto kern = pb::tile_kernel_i8<T, S, KERNEL, MODE, CL>;
+            if constexpr (sizeof(T) == 8 && S == 7 && CL == 1) {
+                if (ctx->i8_a_via_tmem != 0) { kern = pb::tile_kernel_i8<T, S, KERNEL, MODE, CL, true>; }  // doubly-read A planes through tensor memory
+            }
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
             if constexpr (CL == 1) {
                 kern<<<grid, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(p);
@@ -1575,7 +1578,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 ctx->virtual_skew = static_cast<int>(value);
             }
             return;
-        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain" && k != "tile_stats") {
+        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain" && k != "tile_stats" && k != "i8_a_via_tmem") {
             throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
         }
         for_all_members(ctx, [&](plssvm_b200_ctx *c) {
@@ -1601,6 +1604,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 c->fp32_fast_drain = value != 0;
             } else if (k == "tile_stats") {
                 c->tile_stats = value != 0;
+            } else if (k == "i8_a_via_tmem") {
+                c->i8_a_via_tmem = value != 0;
             }
         });
     });

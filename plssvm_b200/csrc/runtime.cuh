@@ -176,6 +176,7 @@ struct plssvm_b200_ctx {
     int linear_factorized = 0;   // 1: linear-kernel matvec as X (X^T v) (two streaming passes) instead of the implicit tiles
     int balance = 1;             // several ranks: re-cut the tile shares from the measured tile-kernel rates every `balance_interval` iterations
     int balance_interval = 8;
+    int i8_a_via_tmem = 0;       // experiment: fp64 int8-slice tiles read the doubly-used A planes from tensor memory (tcgen05.cp + TS-form MMA)
     int tile_stats = 0;          // profiling: per-role wait-cycle counters of the int8-slice tile kernel (synchronises after every tile launch)
     int fp32_fast_drain = 1;     // fp32 int8-slice epilogue: release TMEM before the fp64 -> fp32 conversion (0: the round-1 order, for A/B measurements)
     int virtual_skew = 0;        // testing aid (virtual ranks): percent by which the tile shares grow from the first to the last rank

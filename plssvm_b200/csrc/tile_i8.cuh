@@ -38,6 +38,17 @@
 #include "tile_tf32.cuh"  // tcgen05 helpers
 #include "tile_tf32_2sm.cuh"  // cluster helpers
 
+// How the single-thread roles are entered (see elect_one_sync below): 1 = through elect.sync (tight issue code), 0 = `lane == 0`, -1 = per real
+// type (the default).  Measured on one B200, same box, sustained (profiles/r02/ab_elect_roles.txt): the producer gains a little either way; the
+// MMA issuer gains 2 - 4 % in the fp32 kernel (4 MMAs per step, the issue path mattered) but LOSES 5 % in the fp64 kernel under the 1 kW cap
+// (10 MMAs queued back to back draw more power, the SM clock settles at 1420 instead of 1500 MHz for the same work per clock).
+#ifndef PB_ELECT_PRODUCER
+    #define PB_ELECT_PRODUCER 1
+#endif
+#ifndef PB_ELECT_MMA
+    #define PB_ELECT_MMA -1
+#endif
+
 namespace pb {
 
 constexpr int I8_BK = 64;                                  // bytes (= features) per slab: one SWIZZLE_64B row, two K = 32 MMA steps
@@ -184,6 +195,39 @@ __device__ __forceinline__ void umma_i8(const std::uint32_t tmem_d, const std::u
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the A operand in tensor memory (TS form): `tmem_a` = 8 columns holding 128 rows x 32 bytes
+__device__ __forceinline__ void umma_i8_ts(const std::uint32_t tmem_d, const std::uint32_t tmem_a, const std::uint64_t bdesc, const std::uint32_t idesc, const std::uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared memory -> tensor memory: 128 rows x 256 bits (one K = 32 step of an int8 A operand) described by a matrix descriptor
+__device__ __forceinline__ void tmem_cp_128x256b(const std::uint32_t tmem_dst, const std::uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(tmem_dst), "l"(sdesc) : "memory");
+}
+// One lane of a converged warp (elect.sync).  The single-thread roles branch on THIS predicate, not on `lane == 0`: ptxas then knows that exactly one
+// thread runs the region and issues the tcgen05 / bulk-copy instructions (which take uniform registers) directly; behind `lane == 0` it wraps every
+// one of them in an ELECT / BRA.U.ANY loop (~6 extra instructions per MMA — enough to make the issuing thread the bottleneck of a 10-MMA step).
+__device__ __forceinline__ bool elect_one_sync() {
+    std::uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0u;
+}
+template <bool ELECT>
+__device__ __forceinline__ bool role_entered(const int lane) {
+    if constexpr (ELECT) {
+        return elect_one_sync();
+    } else {
+        return lane == 0;
+    }
+}
 // contiguous global -> shared bulk copy (TMA engine, SASS UBLKCP), completion on an mbarrier
 __device__ __forceinline__ void bulk_load(const std::uint32_t dst, const void *src, const std::uint32_t bytes, const std::uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -225,7 +269,7 @@ __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __h
 // planes and the two of a cluster column the same B planes, so every CTA fetches only one half of the planes of its A block and of its B block and
 // TMA multicasts it to its mate — half the L2 -> SM traffic per CTA (the single-CTA kernel runs at 92 % of the L2 throughput cap).  A stage is
 // refilled once the MMA warps of all three CTAs that write into or read from it have released it (multicast tcgen05.commit, count 3).
-template <typename T, int S_, int KERNEL, int MODE, int CL>
+template <typename T, int S_, int KERNEL, int MODE, int CL, bool TS = false>
 __global__ void __launch_bounds__(I8_THREADS, 1)  // (10 warps = 3 on one SM sub-partition: 170 registers per thread at most)
 tile_kernel_i8(const TileParams<T> p) {
     using L8 = I8Layout<T, S_>;
@@ -297,7 +341,7 @@ tile_kernel_i8(const TileParams<T> p) {
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (role_entered<PB_ELECT_PRODUCER != 0>(lane)) {
             std::uint32_t stage = 0, phase = 0;
             long long w_empty = 0;  // cycles spent waiting for a free ring stage (p.stats)
             const std::uint16_t mask_a = static_cast<std::uint16_t>(3u << (2 * cr));                // the two CTAs of this cluster row
@@ -351,8 +395,9 @@ tile_kernel_i8(const TileParams<T> p) {
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (role_entered<(PB_ELECT_MMA < 0 ? sizeof(T) == 4 : PB_ELECT_MMA != 0)>(lane)) {
             std::uint32_t stage = 0, phase = 0, unit_iter = 0;
+            std::uint32_t kstep_parity = 0;
             long long w_full = 0, w_tempty = 0;  // cycles waiting for operands / for the epilogue to hand the accumulators back (p.stats)
             const long long c_begin = p.stats != nullptr ? clock64() : 0;
             const std::uint16_t mask_rel = static_cast<std::uint16_t>((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));  // this CTA, its row mate, its column mate
@@ -373,6 +418,20 @@ tile_kernel_i8(const TileParams<T> p) {
                         for (std::uint32_t k = 0; k < I8_BK / 32; ++k) {
                             const std::uint64_t koff = static_cast<std::uint64_t>((k * 32) >> 4);  // 32 bytes per K = 32 step inside the swizzle atom
                             const bool first = (ks | k) == 0u;
+                            // Experimental (option "i8_a_via_tmem", fp64 only): the A planes that feed TWO instructions per step (p = 4, 5, 6: 5 - 7 B planes
+                            // = two N <= 256 chunks) are copied shared -> tensor memory once (tcgen05.cp, 24 of the 64 spare columns, double-buffered
+                            // over the steps) and read from there by both instructions — one shared-memory read of the plane instead of two.
+                            constexpr bool a_tmem = TS;
+                            std::uint32_t a_buf = 0;
+                            if constexpr (TS) {
+                                static_assert(!TS || (sizeof(T) == 8 && S == 7 && CL == 1), "A planes through tensor memory: fp64 kernel only");
+                                a_buf = tmem_base + static_cast<std::uint32_t>(S * NH) + (kstep_parity ? 24u : 0u);
+                                kstep_parity ^= 1u;
+                                #pragma unroll
+                                for (int pl = S - 1; pl >= 4; --pl) {
+                                    tmem_cp_128x256b(a_buf + static_cast<std::uint32_t>((pl - 4) * 8), d_a + koff + static_cast<std::uint64_t>((pl * L8::A_SLICE) >> 4));
+                                }
+                            }
                             // slice A_p times the slices B_q, q = S-1-p .. S-1, lands in the accumulators t' = 0 .. p (N <= 256 per instruction)
                             #pragma unroll
                             for (int pp = S - 1; pp >= 0; --pp) {
@@ -380,9 +439,20 @@ tile_kernel_i8(const TileParams<T> p) {
                                 #pragma unroll
                                 for (int c = 0; L8::SLICES_PER_MMA * c < cnt; ++c) {
                                     const int nsl = cnt - L8::SLICES_PER_MMA * c < L8::SLICES_PER_MMA ? cnt - L8::SLICES_PER_MMA * c : L8::SLICES_PER_MMA;
-                                    umma_i8(tmem_base + static_cast<std::uint32_t>(c * L8::SLICES_PER_MMA * NH), d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4),
-                                            d_b + koff + static_cast<std::uint64_t>(((q_lo + L8::SLICES_PER_MMA * c) * L8::B_SLICE) >> 4), i8_idesc(static_cast<std::uint32_t>(nsl * NH)),
-                                            (first && pp == S - 1) ? 0u : 1u);
+                                    const std::uint32_t d_acc = tmem_base + static_cast<std::uint32_t>(c * L8::SLICES_PER_MMA * NH);
+                                    const std::uint64_t bdesc = d_b + koff + static_cast<std::uint64_t>(((q_lo + L8::SLICES_PER_MMA * c) * L8::B_SLICE) >> 4);
+                                    const std::uint32_t idesc = i8_idesc(static_cast<std::uint32_t>(nsl * NH)), acc = (first && pp == S - 1) ? 0u : 1u;
+                                    if constexpr (a_tmem) {
+                                        if (pp >= 4) {
+                                            umma_i8_ts(d_acc, a_buf + static_cast<std::uint32_t>((pp - 4) * 8), bdesc, idesc, acc);
+                                        } else {
+                                            umma_i8(d_acc, d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4), bdesc, idesc, acc);
+                                        }
+                                    } else if (false) {
+                                        umma_i8_ts(d_acc, a_buf + static_cast<std::uint32_t>((pp - 4) * 8), bdesc, idesc, acc);
+                                    } else {
+                                        umma_i8(d_acc, d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4), bdesc, idesc, acc);
+                                    }
                                 }
                             }
                         }
