@@ -134,8 +134,9 @@ void plssvm_b200_rank_range(uint64_t total, int rank, int world_size, uint64_t *
 /* the same with shares proportional to `weights[world_size]` (rate-weighted tile shares, option "balance") */
 void plssvm_b200_weighted_range(uint64_t total, int rank, int world_size, const double *weights, uint64_t *lo, uint64_t *hi);
 /* byte offset of digit `plane` of element (row, feature) in the boxed, pre-swizzled layout of the int8 digit planes: boxes of
- * `box_rows` rows x 64 features x `planes` planes, each box the SWIZZLE_64B shared-memory image tcgen05.mma reads */
-uint64_t plssvm_b200_i8_plane_offset(uint64_t row, uint32_t feature, uint32_t plane, uint32_t planes, uint32_t box_rows, uint32_t slabs);
+ * `box_rows` rows x `slab_bytes` features x `planes` planes, each box the shared-memory image tcgen05.mma reads — K-major rows of 64 bytes with
+ * SWIZZLE_64B (fp64 kernel) or of 32 bytes with SWIZZLE_32B (fp32 kernel) */
+uint64_t plssvm_b200_i8_plane_offset(uint64_t row, uint32_t feature, uint32_t plane, uint32_t planes, uint32_t box_rows, uint32_t slabs, uint32_t slab_bytes);
 
 /* ---- datasets ----------------------------------------------------------------------------------------------------
  * Upload (or adopt from device memory when src_on_device != 0) a dense row-major N x d matrix.  The library keeps its

@@ -95,7 +95,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.plssvm_b200_tri_decode.argtypes = [u64, u64, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
     lib.plssvm_b200_rank_range.restype = None
     lib.plssvm_b200_i8_plane_offset.restype = u64
-    lib.plssvm_b200_i8_plane_offset.argtypes = [u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+    lib.plssvm_b200_i8_plane_offset.argtypes = [u64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
     lib.plssvm_b200_rank_range.argtypes = [u64, i32, i32, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     lib.plssvm_b200_dataset_destroy.argtypes = [vp]
     lib.plssvm_b200_cg_step.argtypes = [vp, u64, ctypes.POINTER(u64), ctypes.POINTER(i32)]
@@ -180,9 +180,10 @@ def _row_pointers(X: np.ndarray):
     return (ctypes.c_void_p * X.shape[0])(*[base + i * stride for i in range(X.shape[0])])
 
 
-def i8_plane_offset(row: int, feature: int, plane: int, planes: int, box_rows: int, slabs: int) -> int:
-    """Byte offset of one digit in the boxed, pre-swizzled plane layout of the int8-slice tile kernel."""
-    return int(load_library().plssvm_b200_i8_plane_offset(row, feature, plane, planes, box_rows, slabs))
+def i8_plane_offset(row: int, feature: int, plane: int, planes: int, box_rows: int, slabs: int, slab_bytes: int = 64) -> int:
+    """Byte offset of one digit in the boxed, pre-swizzled plane layout of the int8-slice tile kernel: slabs of 64 features
+    (SWIZZLE_64B rows, fp64 kernel) or of 32 features (SWIZZLE_32B rows, fp32 kernel)."""
+    return int(load_library().plssvm_b200_i8_plane_offset(row, feature, plane, planes, box_rows, slabs, slab_bytes))
 
 
 def broadcast_bytes(raw: bytes, size: int, src: int = 0, device: int = 0) -> bytes:

@@ -53,7 +53,7 @@ struct plssvm_b200_dataset {
     // int8 digit planes (tile_i8.cuh) in the boxed layout of split_i8_kernel, boxes of 128 rows; X_i8b: experimental CTA-pair kernel only (boxes of 64 rows)
     dblock X_i8, X_i8b, rscale;
     std::size_t ld8 = 0;
-    int i8_slices = 0, i8_br_b = 0;
+    int i8_slices = 0, i8_br_b = 0, i8_slab = 0;
     std::uint64_t i8_key = 0;
     int i8_bad_rows = 0;  // rows whose elements are spread over too many orders of magnitude for the automatic choice (split_i8_kernel)
     int pins = 0;         // open CG sessions using the cached operands
@@ -137,17 +137,21 @@ inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl 
 // rows per box of the extra B-operand copy of the digit planes (experimental CTA-pair kernel only); TILE = no extra copy
 template <typename T>
 int i8_br_b_for(const int impl) { return impl == 9 ? 64 : TILE; }
+// bytes (= features) per slab of the plane layout a tile kernel stages: the experimental CTA-pair kernel was written for 64-byte slabs
+template <typename T>
+int i8_slab_for(const int impl) { return impl == 9 ? 64 : pb::I8<T>::BK; }
 
 // rows -> int8 digit planes + row scales (tile_i8.cuh)
 template <typename T>
 void run_split_i8(plssvm_b200_ctx *ctx, const int slices, const T *X, const std::size_t rows, const std::size_t d, const std::size_t ld, std::int8_t *planes_a,
-                  std::int8_t *planes_b, const int br_b, const std::size_t ld8, T *rscale, int *bad_rows, const T *mean, cudaStream_t st) {
+                  std::int8_t *planes_b, const int br_b, const std::size_t ld8, T *rscale, int *bad_rows, const T *mean, const int slab, cudaStream_t st) {
     const unsigned grid = static_cast<unsigned>(rows_i8(rows) / 8);  // incl. the padding rows of the last box, which get zero digits
-    const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), slabs = static_cast<std::uint32_t>(ld8 / 64);
+    const std::uint32_t d32 = static_cast<std::uint32_t>(d), ld32 = static_cast<std::uint32_t>(ld), slab_w = static_cast<std::uint32_t>(slab);
+    const std::uint32_t slabs = static_cast<std::uint32_t>(ld8) / slab_w;
     if (slices == pb::I8<T>::S) {
-        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, static_cast<std::uint32_t>(br_b), slabs, rscale, bad_rows, mean);
+        pb::split_i8_kernel<T, pb::I8<T>::S><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, static_cast<std::uint32_t>(br_b), slabs, rscale, bad_rows, mean, slab_w);
     } else {
-        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, static_cast<std::uint32_t>(br_b), slabs, rscale, bad_rows, mean);
+        pb::split_i8_kernel<T, pb::I8<T>::S_EXACT><<<grid, 256, 0, st>>>(X, rows, d32, ld32, planes_a, planes_b, static_cast<std::uint32_t>(br_b), slabs, rscale, bad_rows, mean, slab_w);
     }
     PB_CUDA(cudaGetLastError());
     ctx->tm.kernel_launches++;
@@ -208,8 +212,8 @@ operand<T> prepare_operand(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, plssvm
         op.sq = static_cast<const T *>(ds->sq_c.p);
     }
     if (is_i8(impl)) {
-        const int slices = i8_slices_for<T>(impl), br_b = i8_br_b_for<T>(impl);
-        if (ds->X_i8.p == nullptr || ds->i8_slices != slices || ds->i8_br_b != br_b || ds->i8_key != key) {
+        const int slices = i8_slices_for<T>(impl), br_b = i8_br_b_for<T>(impl), slab = i8_slab_for<T>(impl);
+        if (ds->X_i8.p == nullptr || ds->i8_slices != slices || ds->i8_br_b != br_b || ds->i8_key != key || ds->i8_slab != slab) {
             if (ds->X_i8.p != nullptr) { require_unpinned(ds, "splitting it into other digit planes"); }
             ds->ld8 = pitch_i8(ds->d);
             const std::size_t plane_bytes = static_cast<std::size_t>(slices) * rows_i8(ds->N) * ds->ld8;
@@ -223,13 +227,14 @@ operand<T> prepare_operand(plssvm_b200_ctx *ctx, plssvm_b200_dataset *ds, plssvm
             int *bad_d = reinterpret_cast<int *>(static_cast<T *>(ds->rscale.p) + ds->N);  // scratch word behind the scales
             PB_CUDA(cudaMemsetAsync(bad_d, 0, sizeof(int), st));
             std::int8_t *pa = static_cast<std::int8_t *>(ds->X_i8.p);
-            run_split_i8<T>(ctx, slices, X, ds->N, ds->d, ds->ld, pa, br_b != TILE ? static_cast<std::int8_t *>(ds->X_i8b.p) : pa, br_b, ds->ld8, static_cast<T *>(ds->rscale.p), bad_d, mean, st);
+            run_split_i8<T>(ctx, slices, X, ds->N, ds->d, ds->ld, pa, br_b != TILE ? static_cast<std::int8_t *>(ds->X_i8b.p) : pa, br_b, ds->ld8, static_cast<T *>(ds->rscale.p), bad_d, mean, slab, st);
             int *h = static_cast<int *>(ctx->pinned) + 512;  // second half of the pinned block (the first holds the CG state read-back)
             PB_CUDA(cudaMemcpyAsync(h, bad_d, sizeof(int), cudaMemcpyDeviceToHost, st));
             PB_CUDA(cudaStreamSynchronize(st));
             ds->i8_bad_rows = *h;
             ds->i8_slices = slices;
             ds->i8_br_b = br_b;
+            ds->i8_slab = slab;
             ds->i8_key = key;
         }
         op.i8 = static_cast<const std::int8_t *>(ds->X_i8.p);
@@ -671,8 +676,18 @@ plssvm_b200_dataset *dataset_create_rank(plssvm_b200_ctx *ctx, const host_matrix
         const bool sharded = G > 1 && ctx->comm != nullptr && host.valid() && ctx->shard_upload != 0;
         const std::size_t share = sharded ? (N + G - 1) / G : N;  // rows per rank (the last share may be short; X is allocated for G full shares)
         const std::size_t rows_alloc = sharded ? share * G : N;
-        blk_alloc(ctx, ds->X, rows_alloc * ds->ld * sizeof(T));
-        blk_alloc(ctx, ds->sq, N * sizeof(T));
+        {   // allocate, then make sure every device of a group got its memory before anyone enters the all-gather / broadcast
+            std::exception_ptr err;
+            try {
+                blk_alloc(ctx, ds->X, rows_alloc * ds->ld * sizeof(T));
+                blk_alloc(ctx, ds->sq, N * sizeof(T));
+            } catch (...) {
+                err = std::current_exception();
+            }
+            const bool all_ok = group_all_ok(ctx, !err);
+            if (err) { std::rethrow_exception(err); }
+            if (!all_ok) { throw api_error(PLSSVM_B200_ERR_CUDA, "another device of the group failed to allocate the data set"); }
+        }
         T *X = static_cast<T *>(ds->X.p);
         const nccl_api *nccl = (G > 1 && ctx->comm != nullptr) ? &nccl_api::get() : nullptr;
         if (dev_src != nullptr) {
@@ -814,7 +829,17 @@ struct cg_session : cg_session_base {
         PB_CUDA(cudaGetLastError());
         ctx->tm.kernel_launches += 2;
 
-        mv = std::make_unique<matvec_plan<T>>(ctx, ds, kp, q_full.p, &state.p->QA_cost, T(1) / cost, &state.p->done);
+        {   // operands and the partial buffer are allocated here: every device of a group must have succeeded before the first all-reduce
+            std::exception_ptr err;
+            try {
+                mv = std::make_unique<matvec_plan<T>>(ctx, ds, kp, q_full.p, &state.p->QA_cost, T(1) / cost, &state.p->done);
+            } catch (...) {
+                err = std::current_exception();
+            }
+            const bool all_ok = group_all_ok(ctx, !err);
+            if (err) { std::rethrow_exception(err); }
+            if (!all_ok) { throw api_error(PLSSVM_B200_ERR_CUDA, "another device of the group failed to set up the CG solve"); }
+        }
         ctx->tm.matvec_flops = static_cast<double>(ds->d) * static_cast<double>(n) * (static_cast<double>(n) + 1.0);
         ctx->tm.cg_epsilon = static_cast<double>(eps);
 
@@ -1194,7 +1219,8 @@ void predict_rank(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alpha,
                 pt.sq = stage_sq[buf];
                 if (tiles && is_i8(impl)) {
                     if (auto_i8) { PB_CUDA(cudaMemsetAsync(bad_d, 0, sizeof(int), st)); }
-                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], stage_i8[buf], TILE, ld8, stage_sc[buf], auto_i8 ? bad_d : nullptr, nullptr, st);
+                    run_split_i8<T>(ctx, i8_slices_for<T>(impl), stage_X[buf], mb, sv->d, sv->ld, stage_i8[buf], stage_i8[buf], TILE, ld8, stage_sc[buf], auto_i8 ? bad_d : nullptr, nullptr,
+                                    i8_slab_for<T>(impl), st);
                     pt.i8 = pt.i8b = stage_i8[buf];
                     pt.scale = stage_sc[buf];
                     pt.ld8 = static_cast<std::uint32_t>(ld8);
@@ -1684,8 +1710,8 @@ void plssvm_b200_rank_range(uint64_t total, int rank, int world_size, uint64_t *
 void plssvm_b200_weighted_range(uint64_t total, int rank, int world_size, const double *weights, uint64_t *lo, uint64_t *hi) {
     pb::weighted_range(total, rank, world_size, weights, *lo, *hi);
 }
-uint64_t plssvm_b200_i8_plane_offset(uint64_t row, uint32_t feature, uint32_t plane, uint32_t planes, uint32_t box_rows, uint32_t slabs) {
-    return static_cast<uint64_t>(pb::i8_boxed_offset(static_cast<std::size_t>(row), feature, plane, planes, box_rows, slabs));
+uint64_t plssvm_b200_i8_plane_offset(uint64_t row, uint32_t feature, uint32_t plane, uint32_t planes, uint32_t box_rows, uint32_t slabs, uint32_t slab_bytes) {
+    return static_cast<uint64_t>(pb::i8_boxed_offset(static_cast<std::size_t>(row), feature, plane, planes, box_rows, slabs, slab_bytes));
 }
 
 int plssvm_b200_dataset_destroy(plssvm_b200_dataset *ds) {

@@ -22,7 +22,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <exception>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <thread>
@@ -166,6 +168,11 @@ struct plssvm_b200_ctx {
     // full context of its own device with rank = its index and a communicator from ncclCommInitAll
     std::vector<plssvm_b200_ctx *> members;
     plssvm_b200_ctx *leader = nullptr;
+    // host-side agreement of the member threads before they enter a collective (leader only; see group_all_ok)
+    std::mutex agree_mutex;
+    std::condition_variable agree_cv;
+    int agree_arrived = 0, agree_generation = 0;
+    bool agree_failed = false, agree_result = false;
     bool in_process_group() const { return leader != nullptr && leader->members.size() > 1; }
     // options
     int impl = 0;            // 0 auto, 1 simt, 2 floating-point tensor tiles, 6 int8 slices on tcgen05 (tile_i8.cuh), 7 the same with the exact-input slice count
@@ -334,6 +341,28 @@ void for_each_rank(plssvm_b200_ctx *ctx, F &&f) {
     for (const auto &e : errs) {
         if (e) { std::rethrow_exception(e); }
     }
+}
+
+// Device group only: every member thread reports whether its local preparation (allocations, argument checks) succeeded and learns whether ALL
+// did — called before the first collective of an operation, so that a failure on one device becomes an error on every device instead of the
+// others waiting forever inside NCCL.  (One process per GPU: the ranks are separate processes; a failing rank takes its job down.)
+inline bool group_all_ok(plssvm_b200_ctx *ctx, const bool ok) {
+    if (!ctx->in_process_group()) { return ok; }
+    plssvm_b200_ctx *L = ctx->leader;
+    const int n = static_cast<int>(L->members.size());
+    std::unique_lock<std::mutex> lock(L->agree_mutex);
+    const int gen = L->agree_generation;
+    L->agree_failed = L->agree_failed || !ok;
+    if (++L->agree_arrived == n) {
+        L->agree_result = !L->agree_failed;
+        L->agree_arrived = 0;
+        L->agree_failed = false;
+        ++L->agree_generation;
+        L->agree_cv.notify_all();
+    } else {
+        L->agree_cv.wait(lock, [&] { return L->agree_generation != gen; });
+    }
+    return L->agree_result;
 }
 
 // ---- host rows --------------------------------------------------------------------------------------------------------------------

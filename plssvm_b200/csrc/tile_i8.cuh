@@ -51,7 +51,14 @@
 
 namespace pb {
 
-constexpr int I8_BK = 64;                                  // bytes (= features) per slab: one SWIZZLE_64B row, two K = 32 MMA steps
+constexpr int I8_BK = 64;                                  // bytes (= features) per slab of the fp64 kernel: one SWIZZLE_64B row, two K = 32 MMA steps
+// Slab width of the fp32 kernel (64, or 32 = SWIZZLE_32B rows, one K = 32 step per stage, 9 x 24 KB instead of 4 x 48 KB stages).  The 32-byte
+// layout was built to test whether the MMA issuer's operand waits (13.5 % at C3) were TMA latency with too few bytes in flight: they are not —
+// with twice the stages the waits go UP (22.6 %: one full / empty handshake and one tcgen05.commit per K step) and the kernel is 1.3 % slower
+// (422.6 vs 428.0 TFLOP/s sustained, 485.8 vs 489.3 burst, same box; profiles/r02/ab_fp32_slab_width.txt).  Kept selectable; default 64.
+#ifndef PB_I8_BK_F32
+    #define PB_I8_BK_F32 64
+#endif
 constexpr int I8_THREADS = 320;                            // producer warp, MMA warp, 8 epilogue warps
 constexpr int I8_EPI_THREADS = 256;
 constexpr std::uint32_t I8_TMEM_COLS = 512;
@@ -66,28 +73,28 @@ template <typename T>
 struct I8;
 template <>
 struct I8<double> {
-    static constexpr int S = 7, S_EXACT = 7, NH = 64, AUTO_RANGE = 20;
+    static constexpr int S = 7, S_EXACT = 7, NH = 64, AUTO_RANGE = 20, BK = I8_BK;
 };
 template <>
 struct I8<float> {
-    static constexpr int S = 3, S_EXACT = 4, NH = 128, AUTO_RANGE = 10;
+    static constexpr int S = 3, S_EXACT = 4, NH = 128, AUTO_RANGE = 10, BK = PB_I8_BK_F32;
 };
 template <typename T, int S_>
 struct I8Layout {
-    static constexpr int S = S_, NH = I8<T>::NH;
+    static constexpr int S = S_, NH = I8<T>::NH, BK = I8<T>::BK;
     static constexpr int UNITS = TILE / NH;                     // units per 128 x 128 tile of the schedule
-    static constexpr int A_SLICE = TILE * I8_BK;                // 8 KiB
-    static constexpr int B_SLICE = NH * I8_BK;
+    static constexpr int A_SLICE = TILE * BK;                   // fp64: 8 KiB, fp32: 4 KiB
+    static constexpr int B_SLICE = NH * BK;
     static constexpr int A_BYTES = S * A_SLICE;
     static constexpr int B_BYTES = S * B_SLICE;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // fp64: 84 KiB, fp32: 64 KiB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;       // fp64: 84 KiB, fp32: 48 KiB
     static constexpr int VEC_BYTES = (4 * TILE + 4 * NH + 4 * NH + TILE) * static_cast<int>(sizeof(T));  // row vectors, column vectors, column sums, row sums
-    static constexpr int STAGES = (227 * 1024 - 1024 - VEC_BYTES - 256) / STAGE_BYTES;                   // fp64: 2, fp32: 3
+    static constexpr int STAGES = (227 * 1024 - 1024 - VEC_BYTES - 256) / STAGE_BYTES;                   // fp64: 2, fp32: 4 (S = 3) / 3 (S = 4)
     static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + VEC_BYTES + (2 * STAGES + 2) * 8 + 16;
     static constexpr int SLICES_PER_MMA = 256 / NH;             // B slices one N <= 256 instruction covers
     static constexpr int CPT = NH / 2;                          // columns per epilogue thread
     static_assert(S * NH <= 512, "accumulators must fit into TMEM");
-    static_assert(STAGE_BYTES % 1024 == 0 && STAGES >= 2, "stage layout");
+    static_assert(STAGE_BYTES % 1024 == 0 && STAGES >= 2 && (BK == 32 || BK == 64), "stage layout");
     static_assert(VEC_BYTES % 8 == 0 && CPT % 32 == 0, "epilogue layout");
 };
 
@@ -108,9 +115,12 @@ struct I8Layout {
 // largest one; the automatic kernel choice falls back to the floating-point tensor tiles (DMMA / 3xTF32) for such badly scaled data.
 // Rows containing inf / NaN get a NaN scale, so they poison their results exactly like native floating-point arithmetic would.
 __host__ __device__ __forceinline__ std::size_t i8_boxed_offset(const std::size_t r, const std::uint32_t k, const std::uint32_t p, const std::uint32_t S, const std::uint32_t BR,
-                                                                 const std::uint32_t num_slabs) {
-    const std::uint32_t rr = static_cast<std::uint32_t>(r % BR), kk = k & 63u;
-    return (((r / BR) * num_slabs + (k >> 6)) * S + p) * (static_cast<std::size_t>(BR) * 64u) + rr * 64u + ((((kk >> 4) ^ ((rr >> 1) & 3u)) << 4) | (kk & 15u));
+                                                                 const std::uint32_t num_slabs, const std::uint32_t BK = 64) {
+    // K-major rows of BK bytes; the 16-byte chunks of a row are XOR-swizzled with the address bits the hardware swizzle mode uses:
+    // SWIZZLE_64B (BK = 64): bits 4-5 ^= bits 7-8 = (row / 2) % 4;  SWIZZLE_32B (BK = 32): bit 4 ^= bit 7 = (row / 4) % 2
+    const std::uint32_t rr = static_cast<std::uint32_t>(r % BR), kk = k % BK;
+    const std::uint32_t sw = BK == 64 ? ((rr >> 1) & 3u) : ((rr >> 2) & 1u);
+    return (((r / BR) * num_slabs + k / BK) * S + p) * (static_cast<std::size_t>(BR) * BK) + rr * BK + ((((kk >> 4) ^ sw) << 4) | (kk & 15u));
 }
 
 // `mean` (optional, ld entries, pad columns zero): the digits are those of x - mean, rounded once to T — the rbf kernel is evaluated on data
@@ -118,7 +128,8 @@ __host__ __device__ __forceinline__ std::size_t i8_boxed_offset(const std::size_
 template <typename T, int S>
 __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, const std::size_t rows, const std::uint32_t d, const std::uint32_t ld,
                                                        std::int8_t *__restrict__ planes_a, std::int8_t *__restrict__ planes_b, const std::uint32_t br_b,
-                                                       const std::uint32_t num_slabs, T *__restrict__ rscale, int *__restrict__ bad_rows, const T *__restrict__ mean) {
+                                                       const std::uint32_t num_slabs, T *__restrict__ rscale, int *__restrict__ bad_rows, const T *__restrict__ mean,
+                                                       const std::uint32_t slab_w /* bytes (= features) per slab: 64 or 32 */) {
     const std::size_t row = static_cast<std::size_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= (rows + TILE - 1) / TILE * TILE) { return; }
     const bool pad_row = row >= rows;  // padding rows of the last 128-row box: all digits zero
@@ -145,7 +156,7 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
     const double small = ldexp(1.0, e - I8<T>::AUTO_RANGE);
     if (lane == 0 && !pad_row) { rscale[row] = bad ? static_cast<T>(__longlong_as_double(0x7ff8000000000000ll)) : static_cast<T>(ldexp(1.0, e - 6)); }
     unsigned n_nonzero = 0, n_small = 0;
-    for (std::uint32_t k0 = 4u * lane; k0 < 64u * num_slabs; k0 += 128u) {
+    for (std::uint32_t k0 = 4u * lane; k0 < slab_w * num_slabs; k0 += 128u) {
         long long v[4];
         #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -163,8 +174,8 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
                 word |= (static_cast<std::uint32_t>(a) & 0xFFu) << (8 * j);
                 v[j] = (v[j] - a) >> 8;  // exact
             }
-            *reinterpret_cast<std::uint32_t *>(planes_a + i8_boxed_offset(row, k0, p, S, TILE, num_slabs)) = word;
-            if (planes_b != planes_a) { *reinterpret_cast<std::uint32_t *>(planes_b + i8_boxed_offset(row, k0, p, S, br_b, num_slabs)) = word; }
+            *reinterpret_cast<std::uint32_t *>(planes_a + i8_boxed_offset(row, k0, p, S, TILE, num_slabs, slab_w)) = word;
+            if (planes_b != planes_a) { *reinterpret_cast<std::uint32_t *>(planes_b + i8_boxed_offset(row, k0, p, S, br_b, num_slabs, slab_w)) = word; }
         }
     }
     if (bad_rows != nullptr && !pad_row) {
@@ -182,6 +193,16 @@ __global__ void __launch_bounds__(256) split_i8_kernel(const T *__restrict__ X, 
 __device__ __forceinline__ std::uint64_t umma_desc_sw64(const std::uint32_t smem_addr) {
     return static_cast<std::uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<std::uint64_t>(1) << 16) | (static_cast<std::uint64_t>(512 >> 4) << 32) |
            (static_cast<std::uint64_t>(1) << 46) | (static_cast<std::uint64_t>(4) << 61);
+}
+// the same for rows of BK bytes: 32-byte swizzle (layout type 6), 8-row groups 256 bytes apart
+template <int BK>
+__device__ __forceinline__ std::uint64_t umma_desc_kmajor(const std::uint32_t smem_addr) {
+    if constexpr (BK == 64) {
+        return umma_desc_sw64(smem_addr);
+    } else {
+        return static_cast<std::uint64_t>((smem_addr & 0x3FFFFu) >> 4) | (static_cast<std::uint64_t>(1) << 16) | (static_cast<std::uint64_t>(256 >> 4) << 32) |
+               (static_cast<std::uint64_t>(1) << 46) | (static_cast<std::uint64_t>(6) << 61);
+    }
 }
 // instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 128, N = n
 __host__ __device__ constexpr std::uint32_t i8_idesc(const std::uint32_t n) {
@@ -290,7 +311,7 @@ tile_kernel_i8(const TileParams<T> p) {
     const std::uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const std::uint32_t num_slabs = p.ld8 / I8_BK;
+    const std::uint32_t num_slabs = p.ld8 / L8::BK;
     std::uint32_t crank = 0;
     if constexpr (CL == 4) { crank = cluster_ctarank(); }
     const std::uint32_t cr = crank >> 1, cc = crank & 1u;  // position of this CTA inside the 2 x 2 cluster
@@ -413,9 +434,9 @@ tile_kernel_i8(const TileParams<T> p) {
                         if (p.stats != nullptr) { w_full += clock64() - c1; }
                         tcgen05_fence_after();
                         const std::uint32_t base = smem_u32(stages + stage * L8::STAGE_BYTES);
-                        const std::uint64_t d_a = umma_desc_sw64(base), d_b = umma_desc_sw64(base + L8::A_BYTES);
+                        const std::uint64_t d_a = umma_desc_kmajor<L8::BK>(base), d_b = umma_desc_kmajor<L8::BK>(base + L8::A_BYTES);
                         #pragma unroll
-                        for (std::uint32_t k = 0; k < I8_BK / 32; ++k) {
+                        for (std::uint32_t k = 0; k < L8::BK / 32; ++k) {
                             const std::uint64_t koff = static_cast<std::uint64_t>((k * 32) >> 4);  // 32 bytes per K = 32 step inside the swizzle atom
                             const bool first = (ks | k) == 0u;
                             // Experimental (option "i8_a_via_tmem", fp64 only): the A planes that feed TWO instructions per step (p = 4, 5, 6: 5 - 7 B planes
@@ -442,13 +463,7 @@ tile_kernel_i8(const TileParams<T> p) {
                                     const std::uint32_t d_acc = tmem_base + static_cast<std::uint32_t>(c * L8::SLICES_PER_MMA * NH);
                                     const std::uint64_t bdesc = d_b + koff + static_cast<std::uint64_t>(((q_lo + L8::SLICES_PER_MMA * c) * L8::B_SLICE) >> 4);
                                     const std::uint32_t idesc = i8_idesc(static_cast<std::uint32_t>(nsl * NH)), acc = (first && pp == S - 1) ? 0u : 1u;
-                                    if constexpr (a_tmem) {
-                                        if (pp >= 4) {
-                                            umma_i8_ts(d_acc, a_buf + static_cast<std::uint32_t>((pp - 4) * 8), bdesc, idesc, acc);
-                                        } else {
-                                            umma_i8(d_acc, d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4), bdesc, idesc, acc);
-                                        }
-                                    } else if (false) {
+                                    if (a_tmem && pp >= 4) {  // (compile-time after unrolling)
                                         umma_i8_ts(d_acc, a_buf + static_cast<std::uint32_t>((pp - 4) * 8), bdesc, idesc, acc);
                                     } else {
                                         umma_i8(d_acc, d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4), bdesc, idesc, acc);

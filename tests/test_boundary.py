@@ -88,27 +88,33 @@ def test_rank_ranges_partition_the_triangle_evenly(world):
     assert max(sizes) - min(sizes) <= 1
 
 
-@pytest.mark.parametrize("planes,box_rows", [(7, 128), (7, 64), (3, 128), (3, 64)])
-def test_int8_plane_layout_is_a_bijection_of_swizzled_boxes(planes, box_rows):
+@pytest.mark.parametrize("planes,box_rows,slab", [(7, 128, 64), (7, 64, 64), (3, 128, 64), (3, 64, 64), (3, 128, 32), (4, 128, 32)])
+def test_int8_plane_layout_is_a_bijection_of_swizzled_boxes(planes, box_rows, slab):
     """The digit planes are stored as contiguous operand boxes that already are the shared-memory image tcgen05.mma expects:
-    box (R, ks) = planes x box_rows x 64 bytes, plane-major; inside a plane K-major rows of 64 bytes whose 16-byte chunks are XOR-swizzled
-    with bits 1..2 of the row (SWIZZLE_64B).  Host-only: the offset function is the single source of truth of kernel and split."""
+    box (R, ks) = planes x box_rows x slab bytes, plane-major; inside a plane K-major rows of `slab` bytes whose 16-byte chunks are XOR-swizzled
+    with the address bits of the hardware mode — SWIZZLE_64B: bits 1..2 of the row, SWIZZLE_32B (fp32 kernel): bit 2 of the row.
+    Host-only: the offset function is the single source of truth of kernel and split."""
     slabs, rows = 3, 2 * box_rows
     seen = set()
     for r in range(rows):
-        for k in range(0, 64 * slabs, 4):  # the split kernel writes 4 consecutive features per store
+        for k in range(0, slab * slabs, 4):  # the split kernel writes 4 consecutive features per store
             for p in range(planes):
-                off = pb.i8_plane_offset(r, k, p, planes, box_rows, slabs)
+                off = pb.i8_plane_offset(r, k, p, planes, box_rows, slabs, slab)
                 assert off % 4 == 0 and off not in seen
                 seen.add(off)
-                box, within = divmod(off, planes * box_rows * 64)
-                assert box == (r // box_rows) * slabs + k // 64
-                plane, in_plane = divmod(within, box_rows * 64)
+                box, within = divmod(off, planes * box_rows * slab)
+                assert box == (r // box_rows) * slabs + k // slab
+                plane, in_plane = divmod(within, box_rows * slab)
                 assert plane == p
-                rr, byte = divmod(in_plane, 64)
+                rr, byte = divmod(in_plane, slab)
                 assert rr == r % box_rows
-                assert byte == ((((k % 64) // 16) ^ ((rr // 2) % 4)) * 16 + k % 16)
-    assert len(seen) == rows * 16 * slabs * planes and max(seen) < planes * rows * 64 * slabs
+                sw = (rr // 2) % 4 if slab == 64 else (rr // 4) % 2
+                assert byte == ((((k % slab) // 16) ^ sw) * 16 + k % 16)
+                # the swizzle is the hardware's: XOR of address bits [4, 4 + log2(slab / 16)) with bits [7, 7 + log2(slab / 16)) of the in-plane address
+                linear = rr * slab + k % slab
+                mask = (slab // 16 - 1) << 4
+                assert in_plane == linear ^ (((linear >> 7) << 4) & mask)
+    assert len(seen) == rows * (slab // 4) * slabs * planes and max(seen) < planes * rows * slab * slabs
 
 
 def test_tile_size_matches_design():
