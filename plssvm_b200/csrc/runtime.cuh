@@ -202,7 +202,7 @@ struct plssvm_b200_ctx {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_copied[2] = { nullptr, nullptr }, ev_computed[2] = { nullptr, nullptr };
     // pinned ring for host rows that are not one pinned block (std::vector<std::vector<T>> rows, pageable flat buffers)
-    static constexpr std::size_t RING_BYTES = std::size_t{ 32 } << 20;
+    static constexpr std::size_t RING_BYTES = std::size_t{ 8 } << 20;  // (pinning host memory costs ~0.3 ms per MB and is serialised across the devices of a group)
     void *ring[2] = { nullptr, nullptr };
     cudaEvent_t ev_ring[2] = { nullptr, nullptr };
     // grow-only device workspaces kept across calls

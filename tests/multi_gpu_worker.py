@@ -68,6 +68,12 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         if not torch.equal(lo, hi):
             failures.append(f"{kernel}: ranks disagree on alpha")
+        # predict: every rank gets the same points, computes its range, and the ranges are exchanged — every rank returns ALL values, equal to the unsharded ones
+        P, _ = make_data(1000, d, 700 + kid, dtype)
+        vals, _ = be.predict_values(X, r1["alpha"], r1["rho"], P, kernel)
+        vals1, _ = single.predict_values(X, r1["alpha"], r1["rho"], P, kernel)
+        if not np.array_equal(vals, vals1):
+            failures.append(f"{kernel}: sharded predict differs from the unsharded one by {np.max(np.abs(vals - vals1)):.3e}")
         if rank == 0:
             print(f"[world {world}] {kernel}/{np.dtype(dtype).name}: iterations {r['iterations']} (single {r1['iterations']})", flush=True)
     dist.barrier()
