@@ -54,8 +54,9 @@ def parse_args():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=int, default=0, help="override the number of data points (development only; marks the line as non-headline)")
     ap.add_argument("--features", type=int, default=0, help="override the number of features (development only)")
-    ap.add_argument("--tile-impl", type=int, default=0, help="0 auto (int8 slices on tcgen05 kind::i8 for both real types), 1 SIMT tiles, 2 fp64 DMMA / fp32 3xTF32 tiles, "
-                    "6 int8-slice tiles, 7 int8-slice tiles with 4 planes for fp32; 4 / 5 / 8 / 9 only in builds with -DPLSSVM_B200_EXPERIMENTAL")
+    ap.add_argument("--tile-impl", type=int, default=0, help="0 auto (int8 slices on tcgen05 kind::i8 for both real types: fp64 on single CTAs, fp32 on CTA pairs), 1 SIMT tiles, 2 fp64 DMMA / fp32 3xTF32 "
+                    "tiles, 6 int8-slice tiles on single CTAs, 7 the same with 4 planes for fp32, 10 int8-slice tiles on CTA pairs (fp64: experimental builds only); "
+                    "4 / 5 / 8 / 9 only in builds with -DPLSSVM_B200_EXPERIMENTAL")
     ap.add_argument("--no-dmma-line", action="store_true", help="fp64 only: skip the short extra run of the native-FP64 DMMA tiles reported under 'fp64_dmma_tiles'")
     ap.add_argument("--linear-factorized", action="store_true", help="linear kernel only: time the factorised X (X^T v) matvec (HBM-bound) instead of the implicit tiles")
     ap.add_argument("--full-solve", action="store_true", help="additionally run the whole fit to eps = 1e-8 (fp64) / 1e-4 (fp32) through the C ABI; with C1 also on the CPU reference")
@@ -225,12 +226,13 @@ def tile_roofline(impl_used, dtype, kernel, mode, achieved, avg_launch_ms, launc
     fp_pipe = float(pk.get("dmma_tflops_sustained_3s", 37.0)) if f64 else float(pk.get("cublas_sgemm_tf32_random_tflops_sustained_4s", 770.0)) / 3.0
     out = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "avg_launch_ms": avg_launch_ms, "launches_timed": int(launches), "flops_per_launch": flops_per_launch,
            "traffic": traffic}
-    if impl_used in (6, 7, 8, 9):
+    if impl_used in (6, 7, 8, 9, 10):
         products = 28.0 if f64 else (10.0 if impl_used == 7 else 6.0)
         planes = 7 if f64 else (4 if impl_used == 7 else 3)
         sus, burst = float(pk.get("i8_mma_n256_random_tops_sustained_3s", 3819.0)) / products, float(pk.get("i8_mma_n256_random_tops_burst", 4425.0)) / products
-        variant = {8: ", 2 x 2 CTA clusters + TMA multicast", 9: ", CTA pairs (cta_group::2)"}.get(impl_used, "")
-        out.update(kernel=f"tile_kernel_i8<{real}, {planes} int8 planes, {kernel}, {mode}> (tcgen05 kind::i8{variant})", peak=sus, frac=achieved / sus, peak_burst=burst,
+        variant = {8: ", 2 x 2 CTA clusters + TMA multicast", 9: ", CTA pairs (cta_group::2)", 10: ", CTA pairs: cta_group::2, M = 256"}.get(impl_used, "")
+        kname = "tile_kernel_i8_pair" if impl_used == 10 else "tile_kernel_i8"
+        out.update(kernel=f"{kname}<{real}, {planes} int8 planes, {kernel}, {mode}> (tcgen05 kind::i8{variant})", peak=sus, frac=achieved / sus, peak_burst=burst,
                    frac_sustained=achieved / sus, frac_burst=achieved / burst, int8_tops=achieved * products, vs_float_pipe_peak=achieved / fp_pipe, float_pipe_peak_tflops=fp_pipe,
                    peak_source=f"int8 tensor pipe / {int(products)} int8 products per {real} product: tcgen05.mma kind::i8 issue-loop peak with random operands, sustained 3 s "
                                f"({pk.get('i8_mma_n256_random_tops_sustained_3s', 'nominal 3819')} TOPS) resp. burst ({pk.get('i8_mma_n256_random_tops_burst', 'nominal 4425')} TOPS), measured on "
@@ -478,7 +480,7 @@ def cg_roofline(m, n_gpus):
     traffic = None
     ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(ncu_path) and m["N"] == WORKLOADS[m["workload"]][0] and n_gpus == 1:
-        traffic = json.load(open(ncu_path)).get(m["workload"] + ("_i8" if m["impl_used"] in (6, 7) else ""))
+        traffic = json.load(open(ncu_path)).get(m["workload"] + ("_i8" if m["impl_used"] in (6, 7, 10) else ""))
     return tile_roofline(m["impl_used"], m["dtype"], m["kernel"], "sym", achieved, avg_tile_s * 1e3, m["calls"], m["F"] / n_gpus, traffic)
 
 
@@ -611,7 +613,7 @@ def run_ours(args):
     if rk.n_gpus == 1 and headline and args.workload == "C2" and not args.no_extra and not args.linear_factorized:
         extras = extra_workloads(rk, be, args)
 
-    planes = {6: 7 if dtype == "float64" else 3, 7: 7 if dtype == "float64" else 4}.get(impl_used)
+    planes = {6: 7 if dtype == "float64" else 3, 7: 7 if dtype == "float64" else 4, 10: 7 if dtype == "float64" else 3}.get(impl_used)
     line = {
         "metric": "cg_matvec_tflops", "value": m["value"], "unit": "TFLOP/s", "n_gpus": rk.n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",

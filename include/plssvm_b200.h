@@ -55,7 +55,8 @@ typedef struct plssvm_b200_timings {
     double h2d_bytes;
     double d2h_bytes;
     int impl_used;            /* 1 = SIMT FMA tiles, 2 = floating-point tensor tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32), 3 = factorised linear,
-                               * 6 / 7 = int8-slice tcgen05 tiles (fp32: 3 / 4 digit planes); experimental builds only: 4 / 5 fp32 3xTF32 variants,
+                               * 6 / 7 = int8-slice tcgen05 tiles (fp32: 3 / 4 digit planes), 10 = int8-slice tiles on CTA pairs (the fp32 default
+                               * when the A operand has at least 256 rows); experimental builds only: 4 / 5 fp32 3xTF32 variants,
                                * 8 / 9 int8-slice variants on CTA clusters / CTA pairs (see "impl" below) */
     int n_devices;            /* devices (ranks) that took part in the call */
     uint64_t cg_iterations;     /* min(iter + 1, max_iter) as the reference reports it (gpu_csvm.hpp:639,646) */
@@ -90,7 +91,8 @@ const char *plssvm_b200_last_error(void);
 /* tuning / debugging knobs: "impl" — tile kernel of the implicit matvec / predict contraction: 0 auto (int8-slice tcgen05 tiles;
  * the floating-point tensor tiles for more than 16384 features or badly scaled rows), 1 SIMT FMA tiles, 2 floating-point tensor
  * tiles (fp64: TMA + DMMA, fp32: tcgen05 3xTF32), 6 int8 slices on tcgen05 kind::i8 with exact int32 accumulation (fp64: 7 slices =
- * 54 bits, fp32: 3 slices = 22 bits), 7 the same with 4 slices (30 bits) for fp32; only in builds with -DPLSSVM_B200_EXPERIMENTAL
+ * 54 bits, fp32: 3 slices = 22 bits), 7 the same with 4 slices (30 bits) for fp32, 10 the kernel of 6 on CTA pairs (tcgen05.mma.cta_group::2,
+ * tile_i8_pair.cuh; fp64: experimental builds only, otherwise it resolves to 6); only in builds with -DPLSSVM_B200_EXPERIMENTAL
  * (measured-but-not-faster variants kept for reference, bit-identical results): 4 / 5 fp32 3xTF32 variants (CTA pair / 128x256),
  * 8 / 9 variants of 6 (2 x 2 CTA clusters with TMA multicast / fp32 CTA pairs with cta_group::2); "max_ctas" (debugging: cap the
  * number of persistent CTAs of the tile kernels, 0 = one per SM); "check_interval" (CG iterations between host polls),
@@ -103,6 +105,8 @@ const char *plssvm_b200_last_error(void);
  * "shard_upload" (0/1, default 1; several devices / ranks: each uploads 1 / world of the rows, NCCL all-gather);
  * "tile_stats" (0/1, profiling: per-role wait-cycle counters of the int8-slice tile kernel, see plssvm_b200_timings), "fp32_fast_drain" (0/1,
  * default 1; A/B switch of the fp32 epilogue: release TMEM before / after the fp64 -> fp32 conversion, bit-identical results),
+ * "fp32_pair" (0/1, default 1; automatic kernel choice for fp32: the int8-slice tiles run on CTA pairs (impl 10: tcgen05.mma.cta_group::2, the two
+ * tensor cores of a pair share the B operand) instead of single CTAs (impl 6) — bit-identical results, measured 4 - 5 % faster at C3),
  * "i8_a_via_tmem" (0/1, default 0; fp64 int8-slice tiles: the A digit planes that feed two MMAs per step are staged in tensor memory with tcgen05.cp
  * and read by TS-form MMAs — bit-identical, measured 4 % slower, kept as an experiment);
  * testing aid on ONE device: "virtual_world" = G, "virtual_rank" = g make the context compute rank g's share of a G-rank run without

@@ -20,6 +20,7 @@
 #include "tile_simt.cuh"
 #include "tile_tf32.cuh"
 #include "tile_i8.cuh"
+#include "tile_i8_pair.cuh"
 #ifdef PLSSVM_B200_EXPERIMENTAL
     #include "tile_tf32_2sm.cuh"
     #include "tile_tf32_n256.cuh"
@@ -126,20 +127,25 @@ constexpr bool EXPERIMENTAL = true;
 constexpr bool EXPERIMENTAL = false;
 #endif
 
+// The CTA-pair int8-slice kernel (impl 10, tile_i8_pair.cuh) is the automatic choice for fp32 (measured 4 - 5 % faster than the single-CTA kernel at
+// C3); the fp64 instantiation is measured SLOWER (88 vs 105 TFLOP/s at C2) and only exists in builds with -DPLSSVM_B200_EXPERIMENTAL.
+template <typename T>
+constexpr bool pair_kernel_built() { return sizeof(T) == 4 || EXPERIMENTAL; }
+
 // number of int8 slices per operand for the tile-kernel choice `impl` (6: default, 7: exact-input count; the same for fp64)
 template <typename T>
 int i8_slices_for(const int impl) { return impl == 7 ? pb::I8<T>::S_EXACT : pb::I8<T>::S; }
 // int8-slice tile kernels: 6 default slice count, 7 exact-input slice count; experimental: 8 default slice count with 2 x 2 CTA clusters + TMA multicast,
-// 9 (fp32) CTA pairs with tcgen05.mma.cta_group::2 (tile_i8_2sm.cuh)
-inline bool is_i8(const int impl) { return impl >= 6 && impl <= 9; }
+// 9 (fp32) CTA pairs with tcgen05.mma.cta_group::2 (tile_i8_2sm.cuh); 10: CTA pairs with the wide-N instructions (tile_i8_pair.cuh), default slice count
+inline bool is_i8(const int impl) { return impl >= 6 && impl <= 10; }
 // kernels whose tile range / ownership is over 256 x 256 super-tiles
-inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8 || impl == 9; }
+inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8 || impl == 9 || impl == 10; }
 // rows per box of the extra B-operand copy of the digit planes (experimental CTA-pair kernel only); TILE = no extra copy
 template <typename T>
 int i8_br_b_for(const int impl) { return impl == 9 ? 64 : TILE; }
 // bytes (= features) per slab of the plane layout a tile kernel stages: the experimental CTA-pair kernel was written for 64-byte slabs
 template <typename T>
-int i8_slab_for(const int impl) { return impl == 9 ? 64 : pb::I8<T>::BK; }
+int i8_slab_for(const int impl) { return impl == 9 ? 64 : (impl == 10 ? pb::I8PairConfig<T>::BK : pb::I8<T>::BK); }
 
 // rows -> int8 digit planes + row scales (tile_i8.cuh)
 template <typename T>
@@ -313,6 +319,35 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
         }
     }
 #endif
+    if constexpr (pair_kernel_built<T>()) {
+    if (impl == 10) {  // int8-slice tiles on CTA pairs (tile_i8_pair.cuh): contiguous operand boxes -> 2-D boxes of 128-byte lines
+        using L8 = pb::I8PairLayout2<T, pb::I8<T>::S>;
+        PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
+        auto line_map = [&](CUtensorMap *tm, const std::int8_t *base, const std::size_t rows, const std::uint32_t box_lines) {
+            const cuuint64_t dims[2] = { 128, static_cast<cuuint64_t>(static_cast<std::size_t>(L8::S) * rows_i8(rows) * p.ld8 / 128) };
+            const cuuint64_t strides[1] = { 128 };
+            const cuuint32_t box[2] = { 128, box_lines };
+            const cuuint32_t estr[2] = { 1, 1 };
+            const CUresult rc = ctx->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<std::int8_t *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS) { throw api_error(PLSSVM_B200_ERR_CUDA, "cuTensorMapEncodeTiled (digit-plane lines) failed with code " + std::to_string(static_cast<int>(rc))); }
+        };
+        CUtensorMap tmA, tmR1, tmBig, tmSmall;
+        const std::size_t rows_a = static_cast<std::size_t>(p.T_rows) * TILE, rows_b = static_cast<std::size_t>(p.T_cols) * TILE;
+        line_map(&tmA, p.A_i8, rows_a, L8::A_BOX_LINES);
+        line_map(&tmR1, p.B_i8, rows_b, L8::R1_BOX_LINES);
+        line_map(&tmBig, p.B_i8, rows_b, L8::BIG_LINES);
+        line_map(&tmSmall, p.B_i8, rows_b, L8::SMALL_LINES);
+        const unsigned max_pairs = static_cast<unsigned>((ctx->max_ctas > 0 ? std::min(ctx->max_ctas, ctx->num_sms) : ctx->num_sms) / 2);
+        const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, std::max(1u, max_pairs)));
+        auto kern = pb::tile_kernel_i8_pair<T, pb::I8<T>::S, KERNEL, MODE>;
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L8::SMEM_BYTES));
+        kern<<<2 * clusters, pb::I8_THREADS, L8::SMEM_BYTES, ctx->stream>>>(tmA, tmR1, tmBig, tmSmall, p);
+        PB_CUDA(cudaGetLastError());
+        ctx->tm.kernel_launches++;
+        return;
+    }
+    }
     if (is_i8(impl)) {  // int8-slice tcgen05 tiles: S exact int32 accumulators in TMEM (fp64: S = 7, units of 128 x 64; fp32: S = 3 or 4, units of 128 x 128)
         PB_REQUIRE(p.A_i8 != nullptr && p.B_i8 != nullptr && p.A_scale != nullptr && p.B_scale != nullptr, "int8-slice tensor path needs the digit planes of both operands");
         auto launch = [&](auto slices, auto cluster) {
@@ -412,14 +447,19 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
 }
 
 template <typename T>
-int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0) {
+int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0, const std::size_t rows = 0) {
     // int8-slice tcgen05 tiles: beyond I8_MAX_FEATURES the int32 accumulators could overflow -> DMMA / 3xTF32 tiles
-    if (is_i8(ctx->impl)) { return features <= pb::I8_MAX_FEATURES ? ((sizeof(T) == 8 && (ctx->impl == 7 || ctx->impl == 9)) ? 6 : ctx->impl) : 2; }
+    if (is_i8(ctx->impl)) {
+        if (features > pb::I8_MAX_FEATURES) { return 2; }
+        if (sizeof(T) == 8 && (ctx->impl == 7 || ctx->impl == 9)) { return 6; }
+        if (ctx->impl == 10 && !pair_kernel_built<T>()) { return 6; }
+        return ctx->impl;
+    }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
     if (ctx->impl != 0) { return ctx->impl; }
-    // auto: int8 slices on tcgen05 (tile_i8.cuh) where the int32 accumulators cannot overflow; callers fall back to 2 for badly scaled
-    // rows: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
-    if (features > 0 && features <= pb::I8_MAX_FEATURES) { return 6; }
+    // auto: int8 slices on tcgen05 where the int32 accumulators cannot overflow (fp32 with at least one 256-row block of the A operand: on CTA
+    // pairs); callers fall back to 2 for badly scaled rows: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
+    if (features > 0 && features <= pb::I8_MAX_FEATURES) { return (sizeof(T) == 4 && ctx->fp32_pair != 0 && rows >= 2 * TILE && ctx->num_sms >= 2) ? 10 : 6; }
     return 2;
 }
 // automatic kernel choice only: the int8-slice tiles are used unless an operand holds badly scaled rows (split_i8_kernel)
@@ -430,7 +470,7 @@ void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p_in, const int imp
     ctx->tm.impl_used = impl;
     TileParams<T> p = p_in;
     p.slow_drain = ctx->fp32_fast_drain != 0 ? 0 : 1;
-    const bool stats = ctx->tile_stats != 0 && (impl == 6 || impl == 7);
+    const bool stats = ctx->tile_stats != 0 && (impl == 6 || impl == 7 || impl == 10);
     const std::size_t stat_words = static_cast<std::size_t>(ctx->num_sms) * 8;
     if (stats) {
         p.stats = workspace<unsigned long long>(ctx, plssvm_b200_ctx::WS_STATS, stat_words);
@@ -516,7 +556,7 @@ struct matvec_plan {
         Tb = (n + TILE - 1) / TILE;
         const bool tiles_needed = !(c->linear_factorized != 0 && kp.kernel == pb::K_LINEAR);
         plssvm_b200_dataset *centre = kp.kernel == pb::K_RBF ? data : nullptr;  // rbf: on data centred at its own feature means
-        impl = resolve_impl<T>(c, data->ld);
+        impl = resolve_impl<T>(c, data->ld, data->N - 1);
         operand<T> op;
         if (tiles_needed) {
             op = prepare_operand<T>(c, data, centre, impl, kp.kernel == pb::K_RBF);
@@ -1128,7 +1168,7 @@ void predict_rank(plssvm_b200_ctx *ctx, plssvm_b200_dataset *sv, const T *alpha,
     // rbf: both operands centred at the feature means of the support vectors
     plssvm_b200_dataset *centre = kernel == pb::K_RBF ? sv : nullptr;
     const T *mean = centre != nullptr ? ensure_mean<T>(ctx, centre) : nullptr;
-    int impl = resolve_impl<T>(ctx, sv->ld);
+    int impl = resolve_impl<T>(ctx, sv->ld, hi - lo);
     operand<T> svo, pto;
     const bool tiles = kernel != pb::K_LINEAR;
     if (tiles) {
@@ -1579,9 +1619,9 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(handle_live(ctx) && key != nullptr, "ctx (NULL or destroyed) or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            const bool known = value == 0 || value == 1 || value == 2 || value == 6 || value == 7 || (EXPERIMENTAL && (value == 4 || value == 5 || value == 8 || value == 9));
-            PB_REQUIRE(known, std::string("impl must be 0 (auto), 1 (simt), 2 (floating-point tensor tiles), 6 (int8-slice tcgen05 tiles) or 7 (int8-slice tiles with the exact-input "
-                                          "slice count: fp32 4 instead of 3 slices)") +
+            const bool known = value == 0 || value == 1 || value == 2 || value == 6 || value == 7 || value == 10 || (EXPERIMENTAL && (value == 4 || value == 5 || value == 8 || value == 9));
+            PB_REQUIRE(known, std::string("impl must be 0 (auto), 1 (simt), 2 (floating-point tensor tiles), 6 (int8-slice tcgen05 tiles), 7 (int8-slice tiles with the exact-input "
+                                          "slice count: fp32 4 instead of 3 slices) or 10 (int8-slice tiles on CTA pairs, cta_group::2 with the wide-N instructions)") +
                                   (EXPERIMENTAL ? "; experimental: 4 (fp32: CTA-pair 3xTF32), 5 (fp32: 128x256 3xTF32), 8 (int8-slice tiles, 2 x 2 CTA clusters with TMA multicast), 9 (fp32: "
                                                   "int8-slice tiles on CTA pairs, cta_group::2)"
                                                 : "; 4 / 5 / 8 / 9 need a build with -DPLSSVM_B200_EXPERIMENTAL"));
@@ -1604,7 +1644,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 ctx->virtual_skew = static_cast<int>(value);
             }
             return;
-        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain" && k != "tile_stats" && k != "i8_a_via_tmem") {
+        } else if (k != "verbose" && k != "ignore_convergence" && k != "linear_factorized" && k != "balance" && k != "shard_upload" && k != "fp32_fast_drain" && k != "tile_stats" && k != "i8_a_via_tmem" && k != "fp32_pair") {
             throw api_error(PLSSVM_B200_ERR_INVALID, "unknown option '" + k + "'");
         }
         for_all_members(ctx, [&](plssvm_b200_ctx *c) {
@@ -1632,6 +1672,8 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
                 c->tile_stats = value != 0;
             } else if (k == "i8_a_via_tmem") {
                 c->i8_a_via_tmem = value != 0;
+            } else if (k == "fp32_pair") {
+                c->fp32_pair = value != 0;
             }
         });
     });

@@ -175,7 +175,7 @@ struct plssvm_b200_ctx {
     bool agree_failed = false, agree_result = false;
     bool in_process_group() const { return leader != nullptr && leader->members.size() > 1; }
     // options
-    int impl = 0;            // 0 auto, 1 simt, 2 floating-point tensor tiles, 6 int8 slices on tcgen05 (tile_i8.cuh), 7 the same with the exact-input slice count
+    int impl = 0;            // 0 auto, 1 simt, 2 floating-point tensor tiles, 6 int8 slices on tcgen05 (tile_i8.cuh), 7 the same with the exact-input slice count, 10 int8 slices on CTA pairs (tile_i8_pair.cuh)
     int check_interval = 0;  // 0 = auto
     int verbose = 0;
     int ignore_convergence = 0;  // benchmarking: never set the convergence flag, so exactly the requested number of iterations runs
@@ -185,6 +185,7 @@ struct plssvm_b200_ctx {
     int balance_interval = 8;
     int i8_a_via_tmem = 0;       // experiment: fp64 int8-slice tiles read the doubly-used A planes from tensor memory (tcgen05.cp + TS-form MMA)
     int tile_stats = 0;          // profiling: per-role wait-cycle counters of the int8-slice tile kernel (synchronises after every tile launch)
+    int fp32_pair = 1;           // automatic kernel choice, fp32: int8-slice tiles on CTA pairs (impl 10) instead of single CTAs (impl 6)
     int fp32_fast_drain = 1;     // fp32 int8-slice epilogue: release TMEM before the fp64 -> fp32 conversion (0: the round-1 order, for A/B measurements)
     int virtual_skew = 0;        // testing aid (virtual ranks): percent by which the tile shares grow from the first to the last rank
     int shard_upload = 1;        // several ranks: every rank uploads 1 / world of the rows over its own PCIe link, ncclAllGather over NVLink

@@ -216,6 +216,17 @@ __device__ __forceinline__ void umma_i8(const std::uint32_t tmem_d, const std::u
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 256 (pair), N = n
+__host__ __device__ constexpr std::uint32_t i8_idesc_pair(const std::uint32_t n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24); }
+// the same product issued for a CTA pair (cta_group::2, M = 256): each CTA supplies its 128 rows of A and HALF of the N rows of B
+__device__ __forceinline__ void umma_i8_2sm(const std::uint32_t tmem_d, const std::uint64_t adesc, const std::uint64_t bdesc, const std::uint32_t idesc, const std::uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // the same with the A operand in tensor memory (TS form): `tmem_a` = 8 columns holding 128 rows x 32 bytes
 __device__ __forceinline__ void umma_i8_ts(const std::uint32_t tmem_d, const std::uint32_t tmem_a, const std::uint64_t bdesc, const std::uint32_t idesc, const std::uint32_t accumulate) {
     asm volatile(

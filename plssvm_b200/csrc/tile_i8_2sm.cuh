@@ -36,18 +36,6 @@ struct I8PairLayout {
     static_assert(S * NH <= 512 && STAGE_BYTES % 1024 == 0 && STAGES >= 2, "pair layout");
 };
 
-// instruction descriptor: D = S32, A = B = signed int8, both K-major, M = 256 (pair), N = n
-__host__ __device__ constexpr std::uint32_t i8_idesc_pair(const std::uint32_t n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24); }
-
-__device__ __forceinline__ void umma_i8_2sm(const std::uint32_t tmem_d, const std::uint64_t adesc, const std::uint64_t bdesc, const std::uint32_t idesc, const std::uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
 template <int S_, int KERNEL, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
 tile_kernel_i8_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TileParams<float> p) {

@@ -1,0 +1,485 @@
+// int8-slice tile kernel on CTA pairs WITH the wide-N instructions: tcgen05.mma.cta_group::2.kind::i8, M = 256 (two SMs x 128 rows), N <= 256.
+//
+// Same arithmetic, accumulator layout and epilogue as tile_i8.cuh (results are bit-identical); what changes is how the B operand reaches the
+// tensor cores.  The single-CTA kernel is bound by the shared-memory port of its SM: per 32-feature step the MMAs read
+// 96 KB (fp64) / 40 KB (fp32) of operands and the producer writes 42 / 24 KB into the ring — 154 / 171 B/clk at the tensor pipe's pace against
+// the 128 B/clk the port delivers.  With cta_group::2 the two tensor cores of a pair share the B operand: each CTA supplies only HALF of the N
+// rows of every instruction out of its own shared memory, so the B reads per SM halve (68 / 28 KB of operand reads per step).
+//
+// The wide-N trick (one instruction multiplies A_p with several consecutive B planes that lie side by side in shared memory) needs the B rows
+// of an instruction to be [first half | second half] = [CTA 0 | CTA 1] of the CONCATENATION of its planes, at the SAME shared-memory offset in
+// both CTAs (one descriptor serves the pair).  Layout of a stage's B area that achieves this for every instruction of a step:
+//   * region 1, plane-sized slots j = 0 .. S - HALF - 1 (HALF = half the planes of a full N = 256 instruction): CTA 0 holds plane j, CTA 1 plane
+//     j + HALF.  A full instruction over planes q .. q + 2 HALF - 1 points at slot q: CTA 0 supplies planes q .. q + HALF - 1, CTA 1 the rest.
+//   * region 2, one piece per partial instruction (the nsl < 2 HALF planes S - nsl .. S - 1 that end a plane's range): CTA r holds the rows
+//     [r nsl NH / 2, (r + 1) nsl NH / 2) of that concatenation.
+// fp64 (S = 7, NH = 64): 5 planes + 192 rows = 32 KB of B per slab and CTA (single-CTA kernel: 28 KB) -> 110 KB through the port per step
+// = 123 B/clk; fp32 (S = 3, NH = 128): 2 planes + 64 rows = 20 KB (24 KB) -> 50 KB per step = 130 B/clk.
+//   * both CTAs: warp 0 = TMA producer — the pre-swizzled boxes of split_i8_kernel are contiguous, so every piece is one 2-D box of 128-byte lines
+//     (cp.async.bulk.tensor ... cta_group::2, completing on the LEADER's mbarrier); warps 2-9 = epilogue over their own 128 accumulator rows
+//   * leader CTA (cluster rank 0): warp 1 issues the MMAs for the pair; tcgen05.commit ... multicast::cluster releases the ring stage /
+//     publishes the accumulators in BOTH CTAs; the epilogue warps of both CTAs hand TMEM back by arriving on the leader's mbarrier
+// Work items are 256 x 256 super-tiles (schedule, ownership and reduction as for the other CTA-pair kernels, tile_shift = 1): CTA r owns tile row
+// 2 I2 + r, the pair walks the two tile columns (and the 128 / NH units of each) one after the other.  In a diagonal super-tile the strictly-upper
+// tile is computed but never stored.
+// Replaces device_kernel_{linear,polynomial,rbf} (reference svm_kernel.cu:17-222) and device_kernel_predict_* (predict_kernel.cu:32-74).
+#pragma once
+
+#include "tile_i8.cuh"
+
+namespace pb {
+
+// Compile-time configuration of the pair kernel per real type (A/B builds override them with -D...):
+//   slab width BK (bytes = features per ring stage: 64 = SWIZZLE_64B rows / two K = 32 steps, 32 = SWIZZLE_32B rows / one step — twice the stages, finer refill
+//   granularity: what a 2-stage ring of 88 KB needs) and WIDE (1: the wide-N layout above; 0: one instruction per plane pair, N = NH, every CTA stages
+//   only its NH / 2 rows of each B plane — the least L2 -> shared-memory traffic, but S (S + 1) / 2 instructions that each re-read an A plane).
+#ifndef PB_PAIR_BK_F64
+    #define PB_PAIR_BK_F64 32
+#endif
+#ifndef PB_PAIR_BK_F32
+    #define PB_PAIR_BK_F32 64
+#endif
+#ifndef PB_PAIR_WIDE_F64
+    #define PB_PAIR_WIDE_F64 1
+#endif
+#ifndef PB_PAIR_WIDE_F32
+    #define PB_PAIR_WIDE_F32 0
+#endif
+template <typename T>
+struct I8PairConfig;
+template <>
+struct I8PairConfig<double> {
+    static constexpr int BK = PB_PAIR_BK_F64;
+    static constexpr bool WIDE = PB_PAIR_WIDE_F64 != 0;
+};
+template <>
+struct I8PairConfig<float> {
+    static constexpr int BK = PB_PAIR_BK_F32;
+    static constexpr bool WIDE = PB_PAIR_WIDE_F32 != 0;
+};
+
+template <typename T, int S_>
+struct I8PairLayout2 {
+    static constexpr int S = S_, NH = I8<T>::NH, BK = I8PairConfig<T>::BK;
+    static constexpr bool WIDE = I8PairConfig<T>::WIDE;
+    static constexpr int UNITS = TILE / NH;
+    static constexpr int SPM = WIDE ? 256 / NH : 1;              // B planes one instruction covers (wide: N = 256)
+    static constexpr int HALF = SPM / 2;                         // wide: ... of which each CTA supplies this many
+    static constexpr int A_SLICE = TILE * BK;                    // BK = 64: 8 KiB
+    static constexpr int B_SLICE = NH * BK;                      // BK = 64: fp64 4 KiB, fp32 8 KiB
+    static constexpr int HALF_SLICE = B_SLICE / 2;               // NH / 2 rows of one plane: the granule of region 2 / the slot of the narrow layout
+    static constexpr int A_BYTES = S * A_SLICE;
+    static constexpr int R1_SLOTS = WIDE ? S - HALF : S;         // narrow: slot q = this CTA's NH / 2 rows of plane q
+    static constexpr int R1_BYTES = R1_SLOTS * (WIDE ? B_SLICE : HALF_SLICE);
+    static constexpr int R2_BYTES = WIDE ? HALF_SLICE * (SPM * (SPM - 1) / 2) : 0;
+    static constexpr int B_BYTES = R1_BYTES + R2_BYTES;          // wide, BK = 64: fp64 32 KiB, fp32 (S = 3) 20 KiB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;        // wide, BK = 64: fp64 88 KiB, fp32 44 KiB
+    static constexpr int VEC_BYTES = (4 * TILE + 4 * NH + 4 * NH + TILE) * static_cast<int>(sizeof(T));
+    static constexpr int STAGES_FIT = (227 * 1024 - 1024 - VEC_BYTES - 512) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_FIT > 12 ? 12 : STAGES_FIT;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + VEC_BYTES + (2 * STAGES + 2) * 8 + 16;
+    static constexpr int CPT = NH / 2;                           // columns per epilogue thread
+    // 2-D boxes of 128-byte lines (at most 256 lines each)
+    static constexpr int PLANE_LINES = A_SLICE / 128;            // lines per plane of a (row block, slab) box of the plane buffer
+    static constexpr int A_LINES = A_BYTES / 128;
+    static constexpr int A_BOXES = (A_LINES + 255) / 256;        // BK = 64: fp64 2 boxes of 224 lines, fp32 1 box of 192
+    static constexpr int A_BOX_LINES = A_LINES / A_BOXES;
+    static constexpr bool R1_ONE_BOX = WIDE && UNITS == 1;       // NH = 128: the planes of region 1 are contiguous in the source box
+    static constexpr int R1_BOX_LINES = (R1_ONE_BOX ? R1_BYTES : B_SLICE) / 128;
+    static constexpr int BIG_LINES = B_SLICE / 128, SMALL_LINES = HALF_SLICE / 128;
+    // offset of the region-2 piece of the partial instruction over nsl planes
+    __host__ __device__ static constexpr int r2_offset(const int nsl) { return R1_BYTES + HALF_SLICE * (nsl * (nsl - 1) / 2); }
+    static_assert(BK == 64 || BK == 32, "slab width");
+    static_assert(S * NH <= 512 && S >= SPM && (!WIDE || (SPM >= 2 && SPM % 2 == 0)), "accumulators must fit into TMEM; full instructions split evenly over the pair");
+    static_assert(STAGE_BYTES % 1024 == 0 && STAGES >= 2 && HALF_SLICE % 512 == 0, "stage layout");
+    static_assert(A_LINES % A_BOXES == 0 && A_BOX_LINES <= 256 && R1_BOX_LINES <= 256, "box sizes");
+    static_assert(VEC_BYTES % 8 == 0 && CPT % 32 == 0, "epilogue layout");
+};
+
+template <typename T, int S_, int KERNEL, int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
+tile_kernel_i8_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmBig,
+                    const __grid_constant__ CUtensorMap tmSmall, const TileParams<T> p) {
+    using L8 = I8PairLayout2<T, S_>;
+    constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT, SPM = L8::SPM;
+    extern __shared__ unsigned char smem_raw[];
+    if (p.done != nullptr && *p.done != 0) { return; }
+
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    unsigned char *stages = smem;
+    T *s_row = reinterpret_cast<T *>(smem + STAGES * L8::STAGE_BYTES);            // [4][TILE]: q_i, v_i, sq_i, scale_i
+    T *s_col = s_row + 4 * TILE;                                                   // [4][NH]: q_j, v_j, sq_j, scale_j
+    T *s_colsum = s_col + 4 * NH;                                                  // [4][NH]
+    T *s_rowsum = s_colsum + 4 * NH;                                               // [TILE]
+    std::uint64_t *bars = reinterpret_cast<std::uint64_t *>(s_rowsum + TILE);      // full[STAGES], empty[STAGES], tmem_full, tmem_empty
+    std::uint32_t *tmem_slot = reinterpret_cast<std::uint32_t *>(bars + 2 * STAGES + 2);
+    const std::uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES);
+    const std::uint32_t tfull = smem_u32(bars + 2 * STAGES), tempty = smem_u32(bars + 2 * STAGES + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const std::uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const std::uint32_t num_slabs = p.ld8 / L8::BK;
+    const std::uint32_t S_rows = (p.T_rows + 1) >> 1, S_cols = (p.T_cols + 1) >> 1;
+    const std::uint64_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (tid == 0) {
+        #pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);   // leader's only: one arrive.expect_tx, bytes of both CTAs
+            mbar_init(empty0 + 8 * s, 1);  // one multicast commit per phase
+        }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, 2 * (I8_EPI_THREADS / 32));  // leader's only: 8 epilogue warps x 2 CTAs
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(I8_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
+    __syncthreads();     // (redundant after the cluster barrier; racecheck tracks bar.sync only)
+    tcgen05_fence_after();
+    const std::uint32_t tmem_base = *tmem_slot;
+
+    // work item L -> super-tile (I2, J2); this CTA's tile row is I = 2 I2 + rank, the pair's tile columns are 2 J2 and 2 J2 + 1
+    auto decode2 = [&](const std::uint64_t L, std::uint32_t &I2, std::uint32_t &J2) {
+        if constexpr (MODE == MODE_SYM) {
+            tri_decode(S_rows, L, I2, J2);
+        } else {
+            rect_decode(S_rows, S_cols, L, I2, J2);
+        }
+    };
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (role_entered<PB_ELECT_PRODUCER != 0>(lane)) {
+            std::uint32_t stage = 0, phase = 0;
+            long long w_empty = 0;
+            constexpr std::uint32_t BOX_LINES = static_cast<std::uint32_t>(L8::A_LINES);  // 128-byte lines per (row block, slab) box of the plane buffer
+            for (std::uint64_t L = p.tile_lo + cluster_id; L < p.tile_hi; L += num_clusters) {
+                std::uint32_t I2, J2;
+                decode2(L, I2, J2);
+                const std::uint32_t I = 2 * I2 + rank, Il = I < p.T_rows ? I : p.T_rows - 1;  // a padding tile row re-reads the last valid block
+                for (std::uint32_t c = 0; c < 2; ++c) {
+                    const std::uint32_t J = 2 * J2 + c;
+                    if (J >= p.T_cols) { continue; }
+                    for (int h = 0; h < UNITS; ++h) {
+                        const std::uint32_t line_a0 = Il * num_slabs * BOX_LINES;
+                        // first line of (plane 0, row h NH) of column block J's box
+                        const std::uint32_t line_b0 = J * num_slabs * BOX_LINES + static_cast<std::uint32_t>(h * L8::BIG_LINES);
+                        for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
+                            const long long c0 = p.stats != nullptr ? clock64() : 0;
+                            mbar_wait(empty0 + 8 * stage, phase ^ 1u);
+                            if (p.stats != nullptr) { w_empty += clock64() - c0; }
+                            const std::uint32_t dst = smem_u32(stages + stage * L8::STAGE_BYTES);
+                            const std::uint32_t bar = full0 + 8 * stage;
+                            if (leader) { mbar_arrive_expect_tx(bar, 2 * L8::STAGE_BYTES); }
+                            const std::uint32_t leader_bar = bar & TF2_PEER_BIT_MASK;
+                            const std::uint32_t la = line_a0 + ks * BOX_LINES, lb = line_b0 + ks * BOX_LINES;
+                            #pragma unroll
+                            for (int b = 0; b < L8::A_BOXES; ++b) {
+                                tma_load_2d_2sm(dst + b * (L8::A_BYTES / L8::A_BOXES), &tmA, 0, static_cast<int>(la + b * L8::A_BOX_LINES), leader_bar);
+                            }
+                            const std::uint32_t dst_b = dst + L8::A_BYTES;
+                            if constexpr (!L8::WIDE) {
+                                // narrow layout: slot q <- this CTA's NH / 2 rows of plane q
+                                #pragma unroll
+                                for (int q = 0; q < S; ++q) {
+                                    tma_load_2d_2sm(dst_b + q * L8::HALF_SLICE, &tmSmall, 0, static_cast<int>(lb + q * L8::PLANE_LINES + rank * L8::SMALL_LINES), leader_bar);
+                                }
+                            } else {
+                                // region 1: slot j <- plane j + rank HALF (rows of unit h)
+                                if constexpr (L8::R1_ONE_BOX) {
+                                    tma_load_2d_2sm(dst_b, &tmR1, 0, static_cast<int>(lb + rank * L8::HALF * L8::PLANE_LINES), leader_bar);
+                                } else {
+                                    #pragma unroll
+                                    for (int j = 0; j < L8::R1_SLOTS; ++j) {
+                                        tma_load_2d_2sm(dst_b + j * L8::B_SLICE, &tmBig, 0, static_cast<int>(lb + (j + rank * L8::HALF) * L8::PLANE_LINES), leader_bar);
+                                    }
+                                }
+                                // region 2: for nsl = 1 .. SPM - 1 the half-plane granules [rank nsl, (rank + 1) nsl) of the planes S - nsl .. S - 1
+                                #pragma unroll
+                                for (int nsl = 1; nsl < SPM; ++nsl) {
+                                    const std::uint32_t dst_r2 = dst + L8::A_BYTES + L8::r2_offset(nsl);
+                                    const int u0 = static_cast<int>(rank) * nsl;
+                                    int i = 0;
+                                    while (i < nsl) {
+                                        const int u = u0 + i;  // granule u = (plane S - nsl + u / 2, row half u % 2)
+                                        const std::uint32_t src_line = lb + static_cast<std::uint32_t>((S - nsl + (u >> 1)) * L8::PLANE_LINES + (u & 1) * L8::SMALL_LINES);
+                                        if ((u & 1) == 0 && i + 1 < nsl) {  // a whole plane: one big box
+                                            tma_load_2d_2sm(dst_r2 + i * L8::HALF_SLICE, &tmBig, 0, static_cast<int>(src_line), leader_bar);
+                                            i += 2;
+                                        } else {
+                                            tma_load_2d_2sm(dst_r2 + i * L8::HALF_SLICE, &tmSmall, 0, static_cast<int>(src_line), leader_bar);
+                                            i += 1;
+                                        }
+                                    }
+                                }
+                            }
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                    }
+                }
+            }
+            if (p.stats != nullptr) { p.stats[blockIdx.x * 8 + 3] = static_cast<unsigned long long>(w_empty); }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (leader && role_entered<(PB_ELECT_MMA < 0 ? sizeof(T) == 4 : PB_ELECT_MMA != 0)>(lane)) {
+            std::uint32_t stage = 0, phase = 0, unit_iter = 0;
+            long long w_full = 0, w_tempty = 0;
+            const long long c_begin = p.stats != nullptr ? clock64() : 0;
+            for (std::uint64_t L = p.tile_lo + cluster_id; L < p.tile_hi; L += num_clusters) {
+                std::uint32_t I2, J2;
+                decode2(L, I2, J2);
+                for (std::uint32_t c = 0; c < 2; ++c) {
+                    if (2 * J2 + c >= p.T_cols) { continue; }
+                    for (int h = 0; h < UNITS; ++h, ++unit_iter) {
+                        const long long c0 = p.stats != nullptr ? clock64() : 0;
+                        mbar_wait(tempty, (unit_iter & 1u) ^ 1u);  // the epilogues of both CTAs have drained the accumulators of the previous unit
+                        if (p.stats != nullptr) { w_tempty += clock64() - c0; }
+                        tcgen05_fence_after();
+                        for (std::uint32_t ks = 0; ks < num_slabs; ++ks) {
+                            const long long c1 = p.stats != nullptr ? clock64() : 0;
+                            mbar_wait(full0 + 8 * stage, phase);
+                            if (p.stats != nullptr) { w_full += clock64() - c1; }
+                            tcgen05_fence_after();
+                            const std::uint32_t base = smem_u32(stages + stage * L8::STAGE_BYTES);
+                            const std::uint64_t d_a = umma_desc_kmajor<L8::BK>(base), d_b = umma_desc_kmajor<L8::BK>(base + L8::A_BYTES);
+                            #pragma unroll
+                            for (std::uint32_t k = 0; k < L8::BK / 32; ++k) {
+                                const std::uint64_t koff = static_cast<std::uint64_t>((k * 32) >> 4);
+                                const bool first = (ks | k) == 0u;
+                                // slice A_p times the slices B_q, q = S-1-p .. S-1, lands in the accumulators t' = 0 .. p (N <= 256 per instruction)
+                                #pragma unroll
+                                for (int pp = S - 1; pp >= 0; --pp) {
+                                    const int q_lo = S - 1 - pp, cnt = pp + 1;
+                                    #pragma unroll
+                                    for (int cch = 0; SPM * cch < cnt; ++cch) {
+                                        const int nsl = cnt - SPM * cch < SPM ? cnt - SPM * cch : SPM;
+                                        const std::uint32_t d_acc = tmem_base + static_cast<std::uint32_t>(cch * SPM * NH);
+                                        // wide: a full instruction reads region 1 at the slot of its first plane, a partial one its own piece of region 2;
+                                        // narrow: the slot of its plane
+                                        const int b_off = !L8::WIDE ? (q_lo + cch) * L8::HALF_SLICE : (nsl == SPM ? (q_lo + SPM * cch) * L8::B_SLICE : L8::r2_offset(nsl));
+                                        umma_i8_2sm(d_acc, d_a + koff + static_cast<std::uint64_t>((pp * L8::A_SLICE) >> 4), d_b + koff + static_cast<std::uint64_t>(b_off >> 4),
+                                                    i8_idesc_pair(static_cast<std::uint32_t>(nsl * NH)), (first && pp == S - 1) ? 0u : 1u);
+                                    }
+                                }
+                            }
+                            umma_commit_2sm(empty0 + 8 * stage);  // ring stage reusable in both CTAs once these MMAs have read it
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+                        umma_commit_2sm(tfull);  // all S accumulators of this unit complete (both CTAs)
+                    }
+                }
+            }
+            if (p.stats != nullptr) {
+                p.stats[blockIdx.x * 8 + 0] = static_cast<unsigned long long>(clock64() - c_begin);
+                p.stats[blockIdx.x * 8 + 1] = static_cast<unsigned long long>(w_full);
+                p.stats[blockIdx.x * 8 + 2] = static_cast<unsigned long long>(w_tempty);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue (both CTAs): warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns CPT ch .. + CPT - 1 of the unit =====
+        // (identical to tile_kernel_i8's except for the work decomposition and the remote hand-back of TMEM)
+        const int quarter = warp & 3;
+        const int ch = (warp - 2) >> 2;        // column half of the unit
+        const int row = quarter * 32 + lane;   // accumulator row of this thread
+        const int et = tid - 64;               // 0..255 among the epilogue threads
+        std::uint32_t unit_iter = 0;
+        for (std::uint64_t L = p.tile_lo + cluster_id; L < p.tile_hi; L += num_clusters) {
+            std::uint32_t I2, J2;
+            decode2(L, I2, J2);
+            const std::uint32_t I = 2 * I2 + rank, row0 = I * TILE;
+            const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
+            for (std::uint32_t c = 0; c < 2; ++c) {
+                const std::uint32_t J = 2 * J2 + c;
+                if (J >= p.T_cols) { continue; }
+                const bool valid = I < p.T_rows && (MODE == MODE_RECT || J <= I);
+                const bool diag = (MODE == MODE_SYM) && (I == J);
+                T rowacc = T(0);
+                for (int h = 0; h < UNITS; ++h, ++unit_iter) {
+                    const std::uint32_t col0 = J * TILE + h * NH;
+                    if (h == 0 && et < TILE) {
+                        const std::uint32_t gi = row0 + et;
+                        const bool oki = gi < p.n_rows;
+                        s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : T(0);
+                        s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : T(0);
+                        s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : T(0);
+                        s_row[3 * TILE + et] = oki ? p.A_scale[gi] : T(0);
+                    }
+                    if (et >= TILE && et < TILE + NH) {
+                        const int cidx = et - TILE;
+                        const std::uint32_t gj = col0 + cidx;
+                        const bool okj = gj < p.n_cols;
+                        s_col[0 * NH + cidx] = (MODE == MODE_SYM && okj) ? p.q[gj] : T(0);
+                        s_col[1 * NH + cidx] = okj ? p.v[gj] : T(0);
+                        s_col[2 * NH + cidx] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : T(0);
+                        s_col[3 * NH + cidx] = okj ? p.B_scale[gj] : T(0);
+                    }
+                    named_bar_sync(1, I8_EPI_THREADS);
+                    const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row];
+                    const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;  // see tile_kernel_i8
+                    const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
+
+                    const long long c2 = (p.stats != nullptr && tid == 64) ? clock64() : 0;
+                    mbar_wait(tfull, unit_iter & 1u);
+                    if (p.stats != nullptr && tid == 64) { atomicAdd(p.stats + blockIdx.x * 8 + 4, static_cast<unsigned long long>(clock64() - c2)); }
+                    tcgen05_fence_after();
+                    const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * CPT);
+
+                    // phase 1: S int32 diagonals -> one value per element (Horner in fp64 from the least significant diagonal)
+                    T a[CPT];
+                    bool released = false;
+                    if constexpr (sizeof(T) == 4 && S == 3 && CPT == 64) {
+                        if (fold3 && p.slow_drain == 0) {
+                            // fp32 fast drain: raw diagonals into registers, folded to two words per element, TMEM released before any floating-point work
+                            std::uint32_t hi[CPT], lo[CPT];
+                            #pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                std::uint32_t r0[32], r1[32], r2[32];
+                                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(0 * NH + half * 32), r0);
+                                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(1 * NH + half * 32), r1);
+                                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(2 * NH + half * 32), r2);
+                                tmem_ld_wait();
+                                #pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    hi[half * 32 + j] = r2[j] * 256u + r1[j];
+                                    lo[half * 32 + j] = r0[j];
+                                }
+                            }
+                            tcgen05_fence_before();
+                            __syncwarp();
+                            if (lane == 0) { mbar_arrive_cluster(tempty, 0u); }
+                            released = true;
+                            #pragma unroll
+                            for (int j = 0; j < CPT; ++j) { a[j] = static_cast<T>(fma(i32_to_f64(lo[j]), 0.00390625, i32_to_f64(hi[j]))); }
+                        }
+                    }
+                    if (!released) {
+                        #pragma unroll
+                        for (int g = 0; g < CPT / 8; ++g) {
+                            std::uint32_t r[S][8];
+                            #pragma unroll
+                            for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
+                            tmem_ld_wait();
+                            #pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                double s = i32_to_f64(r[0][j]);
+                                #pragma unroll
+                                for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
+                                a[g * 8 + j] = static_cast<T>(s);
+                            }
+                        }
+                        // all of this warp's accumulator reads are done: hand TMEM back to the leader's MMA warp
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive_cluster(tempty, 0u); }
+                    }
+
+                    // phase 2: kernel function and the weighted sums (same instantiation scheme, operation order and rounding as tile_kernel_i8)
+                    auto phase2 = [&](auto deg_tag, auto diag_tag) {
+                        constexpr int DEG = decltype(deg_tag)::value;
+                        constexpr bool DIAG = decltype(diag_tag)::value;
+                        constexpr int V = 16 / static_cast<int>(sizeof(T));
+                        struct alignas(16) vec {
+                            T x[V];
+                        };
+                        #pragma unroll
+                        for (int j0 = 0; j0 < CPT; j0 += V) {
+                            const int c0 = ch * CPT + j0;
+                            const vec scj = *reinterpret_cast<const vec *>(s_col + 3 * NH + c0);
+                            const vec vj = *reinterpret_cast<const vec *>(s_col + 1 * NH + c0);
+                            vec sqj{}, qj{};
+                            if constexpr (KERNEL == K_RBF) { sqj = *reinterpret_cast<const vec *>(s_col + 2 * NH + c0); }
+                            if constexpr (MODE == MODE_SYM) { qj = *reinterpret_cast<const vec *>(s_col + 0 * NH + c0); }
+                            #pragma unroll
+                            for (int u = 0; u < V; ++u) {
+                                const int j = j0 + u;
+                                const T dot = a[j] * (sci * scj.x[u]);
+                                const T kv = kernel_from_dot<KERNEL, T, DEG>(dot, sqi, sqj.x[u], p.kp);
+                                T t = kv;
+                                if constexpr (MODE == MODE_SYM) {
+                                    t = kv + qa - qi - qj.x[u];
+                                    if constexpr (DIAG) {
+                                        if (row == h * NH + c0 + u) { t += p.cost_inv; }
+                                    }
+                                }
+                                rowacc = pb_fma(t, vj.x[u], rowacc);
+                                a[j] = t * vi;  // mirrored contribution of this row to column c0 + u
+                            }
+                        }
+                    };
+                    auto phase2_deg = [&](auto deg_tag) {
+                        if (diag) {
+                            phase2(deg_tag, std::true_type{});
+                        } else {
+                            phase2(deg_tag, std::false_type{});
+                        }
+                    };
+                    if constexpr (KERNEL == K_POLYNOMIAL) {
+                        switch (p.kp.degree) {  // CTA-uniform
+                            case 2: phase2_deg(std::integral_constant<int, 2>{}); break;
+                            case 3: phase2_deg(std::integral_constant<int, 3>{}); break;
+                            default: phase2_deg(std::integral_constant<int, 0>{}); break;
+                        }
+                    } else {
+                        phase2_deg(std::integral_constant<int, 0>{});
+                    }
+                    if constexpr (MODE == MODE_SYM) {
+                        if (!diag) {  // CTA-uniform
+                            #pragma unroll
+                            for (int cc = 0; cc < CPT / 32; ++cc) {
+                                #pragma unroll
+                                for (int step = 16; step >= 1; step >>= 1) {
+                                    const bool upper = (lane & step) != 0;
+                                    #pragma unroll
+                                    for (int k = 0; k < step; ++k) {
+                                        const T send = upper ? a[cc * 32 + k] : a[cc * 32 + k + step];
+                                        const T keep = upper ? a[cc * 32 + k + step] : a[cc * 32 + k];
+                                        a[cc * 32 + k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                                    }
+                                }
+                                s_colsum[quarter * NH + ch * CPT + cc * 32 + lane] = a[cc * 32];
+                            }
+                        }
+                    }
+                    if (h == UNITS - 1 && ch == 1) { s_rowsum[row] = rowacc; }
+                    named_bar_sync(1, I8_EPI_THREADS);
+                    if constexpr (MODE == MODE_SYM) {
+                        if (!diag && valid && et < NH) {
+                            const T s = ((s_colsum[et] + s_colsum[NH + et]) + s_colsum[2 * NH + et]) + s_colsum[3 * NH + et];
+                            const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
+                            p.partial[mslot * TILE + h * NH + et] = (col0 + et < p.n_cols) ? s : T(0);
+                        }
+                    }
+                    if (h == UNITS - 1 && ch == 0 && valid) {
+                        const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
+                        p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : T(0);
+                    }
+                    named_bar_sync(1, I8_EPI_THREADS);
+                }
+            }
+        }
+    }
+
+    // teardown: both CTAs are done with TMEM and with each other's shared memory and barriers
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace pb

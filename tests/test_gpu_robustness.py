@@ -57,8 +57,8 @@ def matvec_errors(be, ex, X, v, kernel, gamma, cost=1.0, expect_impl=None):
         ds.close()
     exact = ex.matvec(kid, X, q, v, float(qa), 1.0 / cost, gamma=gamma)
     plain = ex.reference_arithmetic_matvec(kid, X, q, v, float(qa), 1.0 / cost, np.arange(n), gamma=gamma)
-    if expect_impl is not None:
-        assert impl == expect_impl, (impl, expect_impl)
+    if expect_impl is not None:  # (6 = the int8-slice tiles: for fp32 the automatic choice runs them on CTA pairs, impl 10)
+        assert impl == expect_impl or (expect_impl == 6 and impl == 10 and X.dtype == np.float32), (impl, expect_impl)
     return error_vs_exact(got, exact), error_vs_exact(plain, exact), impl
 
 
@@ -174,6 +174,6 @@ def test_badly_scaled_test_points_through_predict(be, ex, kernel, dtype):
     assert np.all(np.abs(vals - exact)[~ok] <= 64 * np.finfo(dtype).eps * np.sum(np.abs(alpha)) * np.maximum(1.0, np.abs(exact[~ok])))
     # well-scaled points of the same call keep the int8-slice tiles
     vals_ok, _ = be.predict_values(X, alpha, 0.1, np.ascontiguousarray(P[20:120]), kernel)
-    assert be.timings()["fallback_batches"] == 0 and be.timings()["impl_used"] == 6
+    assert be.timings()["fallback_batches"] == 0 and be.timings()["impl_used"] == 6  # (100 points: below the 256 rows the fp32 CTA-pair kernel needs)
     assert np.max(np.abs(vals_ok - exact[20:120])) <= tol
     assert np.array_equal(vals_ok, vals[20:120]) or np.max(np.abs(vals_ok - vals[20:120])) <= tol  # (another tile kernel for the same points: same values to rounding)
