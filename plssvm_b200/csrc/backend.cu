@@ -485,14 +485,21 @@ void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p_in, const int imp
         std::vector<unsigned long long> h(stat_words);
         PB_CUDA(cudaMemcpyAsync(h.data(), p.stats, stat_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         PB_CUDA(cudaStreamSynchronize(ctx->stream));
-        double f[4] = { 0, 0, 0, 0 };
+        double f[7] = { 0, 0, 0, 0, 0, 0, 0 };
         int ctas = 0;
         for (int b = 0; b < ctx->num_sms; ++b) {
             const double total = static_cast<double>(h[b * 8]);
             if (total <= 0.0) { continue; }
             ++ctas;
-            for (int k = 0; k < 4; ++k) { f[k] += static_cast<double>(h[b * 8 + 1 + k]) / total; }
+            for (int k = 0; k < 7; ++k) { f[k] += static_cast<double>(h[b * 8 + 1 + k]) / total; }
         }
+#ifdef PB_TILE_STATS_FINE
+        if (ctas > 0 && ctx->tile_stats >= 2) {  // the epilogue's own split (one thread): wait / drain / vector loads + barriers + stores; the remainder is the kernel function + sums
+            std::fprintf(stderr, "{\"tile_stats\": {\"impl\": %d, \"ctas\": %d, \"mma_wait_operands\": %.4f, \"mma_wait_drain\": %.4f, \"producer_wait\": %.4f, "
+                                 "\"epilogue_wait_accumulators\": %.4f, \"epilogue_drain\": %.4f, \"epilogue_loads_barriers_stores\": %.4f, \"epilogue_math\": %.4f}}\n",
+                         impl, ctas, f[0] / ctas, f[1] / ctas, f[2] / ctas, f[3] / ctas, f[4] / ctas, f[6] / ctas, 1.0 - (f[3] + f[4] + f[6]) / ctas);
+        }
+#endif
         if (ctas > 0) {
             ctx->tm.tile_mma_wait_operands = f[0] / ctas;
             ctx->tm.tile_mma_wait_drain = f[1] / ctas;
@@ -1669,7 +1676,7 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
             } else if (k == "fp32_fast_drain") {
                 c->fp32_fast_drain = value != 0;
             } else if (k == "tile_stats") {
-                c->tile_stats = value != 0;
+                c->tile_stats = static_cast<int>(value);  // 1: counters into the timings; 2: also one JSON line per tile launch on stderr
             } else if (k == "i8_a_via_tmem") {
                 c->i8_a_via_tmem = value != 0;
             } else if (k == "fp32_pair") {

@@ -296,6 +296,224 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // exact int32 -> fp64 on the FP64 add pipe: (2^52 + 2^31 + a) - (2^52 + 2^31)
 __device__ __forceinline__ double i32_to_f64(const std::uint32_t a) { return __hiloint2double(0x43300000, static_cast<int>(a ^ 0x80000000u)) - 4503601774854144.0; }
 
+// ---- the epilogue of one unit, shared by the single-CTA kernel below and the CTA-pair kernel (tile_i8_pair.cuh) ---------------------------------
+// Called by the 8 epilogue warps (warps 2..9 of the CTA; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns CPT ch .. + CPT - 1 of the unit) for unit h
+// of tile (I, J): stages the row / column vectors, waits for the S accumulators, drains them (tcgen05.ld, int32 -> real), hands TMEM back to the MMA
+// warp (PAIR: by a remote arrive on the leader CTA's barrier), evaluates the kernel function and accumulates / stores the v-weighted row sums and the
+// mirrored column sums.  `valid` = false: a padding / strictly-upper tile of a super-tile (computed, never stored).
+template <typename T, int S, int KERNEL, int MODE, bool PAIR>
+__device__ __forceinline__ void i8_epilogue_unit(const TileParams<T> &p, T *s_row, T *s_col, T *s_colsum, T *s_rowsum, const std::uint32_t tmem_base, const std::uint32_t tfull,
+                                                 const std::uint32_t tempty, const std::uint32_t unit_iter, const std::uint32_t I, const std::uint32_t J, const int h,
+                                                 const bool valid, const bool diag, const T qa, T &rowacc) {
+    constexpr int NH = I8<T>::NH, UNITS = TILE / NH, CPT = NH / 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quarter = warp & 3;
+    const int ch = (warp - 2) >> 2;        // column half of the unit
+    const int row = quarter * 32 + lane;   // accumulator row of this thread
+    const int et = tid - 64;               // 0..255 among the epilogue threads
+    const std::uint32_t row0 = I * TILE;
+    // profiling (option "tile_stats"): where ONE epilogue thread spends its cycles — stats[4] waiting for the accumulators and, in builds with
+    // -DPB_TILE_STATS_FINE, [5] drain (tcgen05.ld + fold / Horner + conversion), [7] vector loads, named barriers, partial stores; the remainder of the MMA
+    // issuer's loop time is the kernel function + sums.  Differences of clock64() are accumulated as "- start" / "+ end" (mod 2^64), so that no time
+    // stamp stays live across the register-heavy phases.
+    auto stamp = [&](const int minus, const int plus) {
+#ifdef PB_TILE_STATS_FINE  // (the extra stamps cost the fp32 kernels 1 - 2 %: profiling builds only, -DPB_TILE_STATS_FINE)
+        if (p.stats != nullptr && tid == 64) {
+            const unsigned long long now = static_cast<unsigned long long>(clock64());
+            if (minus >= 0) { atomicAdd(p.stats + blockIdx.x * 8 + minus, 0ull - now); }
+            if (plus >= 0) { atomicAdd(p.stats + blockIdx.x * 8 + plus, now); }
+        }
+#else
+        (void) minus;
+        (void) plus;
+#endif
+    };
+    auto hand_back = [&]() {
+        if constexpr (PAIR) {
+            mbar_arrive_cluster(tempty, 0u);
+        } else {
+            mbar_arrive(tempty);
+        }
+    };
+    const std::uint32_t col0 = J * TILE + h * NH;
+    stamp(7, -1);
+    if (h == 0 && et < TILE) {
+        const std::uint32_t gi = row0 + et;
+        const bool oki = gi < p.n_rows;
+        s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : T(0);
+        s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : T(0);
+        s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : T(0);
+        s_row[3 * TILE + et] = oki ? p.A_scale[gi] : T(0);
+    }
+    if (et >= TILE && et < TILE + NH) {
+        const int c = et - TILE;
+        const std::uint32_t gj = col0 + c;
+        const bool okj = gj < p.n_cols;
+        s_col[0 * NH + c] = (MODE == MODE_SYM && okj) ? p.q[gj] : T(0);
+        s_col[1 * NH + c] = okj ? p.v[gj] : T(0);
+        s_col[2 * NH + c] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : T(0);
+        s_col[3 * NH + c] = okj ? p.B_scale[gj] : T(0);
+    }
+    named_bar_sync(1, I8_EPI_THREADS);
+    const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row];
+    // fp32, S = 3, d <= 1984: the two upper diagonals fit one int32 (|ACC_2| 2^8 + |ACC_1| <= d (2^20 + 2^14) < 2^31), so an element is two
+    // words (fast drain below) and its recombination one IMAD + 3 instead of 5 fp64 operations; the sum is 256 x the value, folded
+    // into the row scale.  Both forms are exact in fp64: bit-identical results.
+    const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;
+    const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
+
+    stamp(-1, 7);  // vector loads + named barrier before the wait
+    const long long c2 = (p.stats != nullptr && tid == 64) ? clock64() : 0;
+    mbar_wait(tfull, unit_iter & 1u);
+    if (p.stats != nullptr && tid == 64) { atomicAdd(p.stats + blockIdx.x * 8 + 4, static_cast<unsigned long long>(clock64() - c2)); }
+    stamp(5, -1);
+    tcgen05_fence_after();
+    const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * CPT);
+
+    // phase 1: S int32 diagonals -> one value per element (Horner in fp64 from the least significant diagonal: every step exact
+    // up to one rounding relative to the running sum)
+    T a[CPT];
+    bool released = false;
+    if constexpr (sizeof(T) == 4 && S == 3 && CPT == 64) {
+        if (fold3 && p.slow_drain == 0) {
+            // fp32 fast drain (measured with tools/tmem_probe: the fp64 -> fp32 conversion runs at ~12 elements / clk / SM and a
+            // tcgen05.ld + wait round trip costs a few hundred cycles, so converting while the accumulators are still held kept the
+            // tensor pipe idle for ~1/3 of a d = 1024 unit).  Here the raw int32 diagonals of all 64 columns are pulled into
+            // registers with two rounds of three 32-column loads, folded to two words per element by integer arithmetic, and TMEM
+            // goes back to the MMA warp BEFORE any floating-point work; the conversion overlaps the next unit's MMAs.
+            std::uint32_t hi[CPT], lo[CPT];
+            #pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                std::uint32_t r0[32], r1[32], r2[32];
+                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(0 * NH + half * 32), r0);
+                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(1 * NH + half * 32), r1);
+                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(2 * NH + half * 32), r2);
+                tmem_ld_wait();
+                #pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    hi[half * 32 + j] = r2[j] * 256u + r1[j];
+                    lo[half * 32 + j] = r0[j];
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) { hand_back(); }
+            released = true;
+            #pragma unroll
+            for (int j = 0; j < CPT; ++j) { a[j] = static_cast<T>(fma(i32_to_f64(lo[j]), 0.00390625, i32_to_f64(hi[j]))); }
+        }
+    }
+    if (!released) {
+        #pragma unroll
+        for (int g = 0; g < CPT / 8; ++g) {
+            std::uint32_t r[S][8];
+            #pragma unroll
+            for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
+            tmem_ld_wait();
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                double s = i32_to_f64(r[0][j]);
+                #pragma unroll
+                for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
+                a[g * 8 + j] = static_cast<T>(s);
+            }
+        }
+        // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) { hand_back(); }
+    }
+
+    stamp(-1, 5);  // accumulators read (and converted)
+    // phase 2: kernel function and the weighted sums.  The loop is instantiated per (polynomial degree, diagonal tile) so that the power
+    // is straight-line code and off-diagonal tiles carry no diagonal test (at d = 1024 the fp32 epilogue, not the tensor pipe, paces
+    // the kernel: profiles/r02/tile_role_stats.jsonl); the column vectors come out of shared memory as 16-byte vectors.  Operation
+    // order and rounding are unchanged.
+    auto phase2 = [&](auto deg_tag, auto diag_tag) {
+        constexpr int DEG = decltype(deg_tag)::value;
+        constexpr bool DIAG = decltype(diag_tag)::value;
+        constexpr int V = 16 / static_cast<int>(sizeof(T));  // elements per 16-byte shared-memory load
+        struct alignas(16) vec {
+            T x[V];
+        };
+        #pragma unroll
+        for (int j0 = 0; j0 < CPT; j0 += V) {
+            const int c0 = ch * CPT + j0;
+            const vec scj = *reinterpret_cast<const vec *>(s_col + 3 * NH + c0);
+            const vec vj = *reinterpret_cast<const vec *>(s_col + 1 * NH + c0);
+            vec sqj{}, qj{};
+            if constexpr (KERNEL == K_RBF) { sqj = *reinterpret_cast<const vec *>(s_col + 2 * NH + c0); }
+            if constexpr (MODE == MODE_SYM) { qj = *reinterpret_cast<const vec *>(s_col + 0 * NH + c0); }
+            #pragma unroll
+            for (int u = 0; u < V; ++u) {
+                const int j = j0 + u;
+                const T dot = a[j] * (sci * scj.x[u]);
+                const T kv = kernel_from_dot<KERNEL, T, DEG>(dot, sqi, sqj.x[u], p.kp);
+                T t = kv;
+                if constexpr (MODE == MODE_SYM) {
+                    t = kv + qa - qi - qj.x[u];
+                    if constexpr (DIAG) {
+                        if (row == h * NH + c0 + u) { t += p.cost_inv; }
+                    }
+                }
+                rowacc = pb_fma(t, vj.x[u], rowacc);
+                a[j] = t * vi;  // mirrored contribution of this row to column c0 + u
+            }
+        }
+    };
+    auto phase2_deg = [&](auto deg_tag) {
+        if (diag) {
+            phase2(deg_tag, std::true_type{});
+        } else {
+            phase2(deg_tag, std::false_type{});
+        }
+    };
+    if constexpr (KERNEL == K_POLYNOMIAL) {
+        switch (p.kp.degree) {  // CTA-uniform
+            case 2: phase2_deg(std::integral_constant<int, 2>{}); break;
+            case 3: phase2_deg(std::integral_constant<int, 3>{}); break;
+            default: phase2_deg(std::integral_constant<int, 0>{}); break;
+        }
+    } else {
+        phase2_deg(std::integral_constant<int, 0>{});
+    }
+    if constexpr (MODE == MODE_SYM) {
+        if (!diag) {  // CTA-uniform
+            // butterfly per 32 columns: after 5 halving steps lane c holds the sum over the warp's 32 rows of column c
+            #pragma unroll
+            for (int cc = 0; cc < CPT / 32; ++cc) {
+                #pragma unroll
+                for (int step = 16; step >= 1; step >>= 1) {
+                    const bool upper = (lane & step) != 0;
+                    #pragma unroll
+                    for (int k = 0; k < step; ++k) {
+                        const T send = upper ? a[cc * 32 + k] : a[cc * 32 + k + step];
+                        const T keep = upper ? a[cc * 32 + k + step] : a[cc * 32 + k];
+                        a[cc * 32 + k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+                    }
+                }
+                s_colsum[quarter * NH + ch * CPT + cc * 32 + lane] = a[cc * 32];
+            }
+        }
+    }
+    stamp(7, -1);
+    if (h == UNITS - 1 && ch == 1) { s_rowsum[row] = rowacc; }
+    named_bar_sync(1, I8_EPI_THREADS);  // column sums of the four row quarters / row sums of the second column half visible
+    if constexpr (MODE == MODE_SYM) {
+        if (!diag && valid && et < NH) {
+            const T s = ((s_colsum[et] + s_colsum[NH + et]) + s_colsum[2 * NH + et]) + s_colsum[3 * NH + et];
+            const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
+            p.partial[mslot * TILE + h * NH + et] = (col0 + et < p.n_cols) ? s : T(0);
+        }
+    }
+    if (h == UNITS - 1 && ch == 0 && valid) {
+        const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
+        p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : T(0);
+    }
+    named_bar_sync(1, I8_EPI_THREADS);  // s_col / s_colsum / s_rowsum consumed before the next unit overwrites them
+    stamp(-1, 7);  // named barriers + partial stores after the sums
+}
+
 // CL = 1: one CTA per tile.  CL = 4: a cluster of 2 x 2 CTAs per 256 x 256 super-tile (launched with cluster dimension 4; the tile range is in
 // super-tiles like the CTA-pair 3xTF32 kernel's): CTA (r, c) computes tile (2 I2 + r, 2 J2 + c); the two CTAs of a cluster row need the same A
 // planes and the two of a cluster column the same B planes, so every CTA fetches only one half of the planes of its A block and of its B block and
@@ -306,7 +524,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1)  // (10 warps = 3 on one SM sub
 tile_kernel_i8(const TileParams<T> p) {
     using L8 = I8Layout<T, S_>;
     static_assert(CL == 1 || CL == 4, "cluster size");
-    constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT;
+    constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES;
     extern __shared__ unsigned char smem_raw[];
     if (p.done != nullptr && *p.done != 0) { return; }
 
@@ -505,190 +723,15 @@ tile_kernel_i8(const TileParams<T> p) {
         __syncwarp();
     } else {
         // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns CPT ch .. + CPT - 1 of the unit =====
-        const int quarter = warp & 3;
-        const int ch = (warp - 2) >> 2;        // column half of the unit
-        const int row = quarter * 32 + lane;   // accumulator row of this thread
-        const int et = tid - 64;               // 0..255 among the epilogue threads
         std::uint32_t unit_iter = 0;
         for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
             std::uint32_t I, J;
             const bool valid = decode(L, I, J);
-            const std::uint32_t row0 = I * TILE;
             const bool diag = (MODE == MODE_SYM) && (I == J);
             const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
             T rowacc = T(0);
             for (int h = 0; h < UNITS; ++h, ++unit_iter) {
-                const std::uint32_t col0 = J * TILE + h * NH;
-                if (h == 0 && et < TILE) {
-                    const std::uint32_t gi = row0 + et;
-                    const bool oki = gi < p.n_rows;
-                    s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : T(0);
-                    s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : T(0);
-                    s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : T(0);
-                    s_row[3 * TILE + et] = oki ? p.A_scale[gi] : T(0);
-                }
-                if (et >= TILE && et < TILE + NH) {
-                    const int c = et - TILE;
-                    const std::uint32_t gj = col0 + c;
-                    const bool okj = gj < p.n_cols;
-                    s_col[0 * NH + c] = (MODE == MODE_SYM && okj) ? p.q[gj] : T(0);
-                    s_col[1 * NH + c] = okj ? p.v[gj] : T(0);
-                    s_col[2 * NH + c] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : T(0);
-                    s_col[3 * NH + c] = okj ? p.B_scale[gj] : T(0);
-                }
-                named_bar_sync(1, I8_EPI_THREADS);
-                const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row];
-                // fp32, S = 3, d <= 1984: the two upper diagonals fit one int32 (|ACC_2| 2^8 + |ACC_1| <= d (2^20 + 2^14) < 2^31), so an element is two
-                // words (fast drain below) and its recombination one IMAD + 3 instead of 5 fp64 operations; the sum is 256 x the value, folded
-                // into the row scale.  Both forms are exact in fp64: bit-identical results.
-                const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;
-                const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
-
-                const long long c2 = (p.stats != nullptr && tid == 64) ? clock64() : 0;
-                mbar_wait(tfull, unit_iter & 1u);
-                if (p.stats != nullptr && tid == 64) { atomicAdd(p.stats + blockIdx.x * 8 + 4, static_cast<unsigned long long>(clock64() - c2)); }
-                tcgen05_fence_after();
-                const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * CPT);
-
-                // phase 1: S int32 diagonals -> one value per element (Horner in fp64 from the least significant diagonal: every step exact
-                // up to one rounding relative to the running sum)
-                T a[CPT];
-                bool released = false;
-                if constexpr (sizeof(T) == 4 && S == 3 && CPT == 64) {
-                    if (fold3 && p.slow_drain == 0) {
-                        // fp32 fast drain (measured with tools/tmem_probe: the fp64 -> fp32 conversion runs at ~12 elements / clk / SM and a
-                        // tcgen05.ld + wait round trip costs a few hundred cycles, so converting while the accumulators are still held kept the
-                        // tensor pipe idle for ~1/3 of a d = 1024 unit).  Here the raw int32 diagonals of all 64 columns are pulled into
-                        // registers with two rounds of three 32-column loads, folded to two words per element by integer arithmetic, and TMEM
-                        // goes back to the MMA warp BEFORE any floating-point work; the conversion overlaps the next unit's MMAs.
-                        std::uint32_t hi[CPT], lo[CPT];
-                        #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            std::uint32_t r0[32], r1[32], r2[32];
-                            tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(0 * NH + half * 32), r0);
-                            tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(1 * NH + half * 32), r1);
-                            tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(2 * NH + half * 32), r2);
-                            tmem_ld_wait();
-                            #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                hi[half * 32 + j] = r2[j] * 256u + r1[j];
-                                lo[half * 32 + j] = r0[j];
-                            }
-                        }
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { mbar_arrive(tempty); }
-                        released = true;
-                        #pragma unroll
-                        for (int j = 0; j < CPT; ++j) { a[j] = static_cast<T>(fma(i32_to_f64(lo[j]), 0.00390625, i32_to_f64(hi[j]))); }
-                    }
-                }
-                if (!released) {
-                    #pragma unroll
-                    for (int g = 0; g < CPT / 8; ++g) {
-                        std::uint32_t r[S][8];
-                        #pragma unroll
-                        for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
-                        tmem_ld_wait();
-                        #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            double s = i32_to_f64(r[0][j]);
-                            #pragma unroll
-                            for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
-                            a[g * 8 + j] = static_cast<T>(s);
-                        }
-                    }
-                    // all of this warp's accumulator reads are done: hand TMEM back to the MMA warp
-                    tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(tempty); }
-                }
-
-                // phase 2: kernel function and the weighted sums.  The loop is instantiated per (polynomial degree, diagonal tile) so that the power
-                // is straight-line code and off-diagonal tiles carry no diagonal test (at d = 1024 the fp32 epilogue, not the tensor pipe, paces
-                // the kernel: profiles/r02/tile_role_stats.jsonl); the column vectors come out of shared memory as 16-byte vectors.  Operation
-                // order and rounding are unchanged.
-                auto phase2 = [&](auto deg_tag, auto diag_tag) {
-                    constexpr int DEG = decltype(deg_tag)::value;
-                    constexpr bool DIAG = decltype(diag_tag)::value;
-                    constexpr int V = 16 / static_cast<int>(sizeof(T));  // elements per 16-byte shared-memory load
-                    struct alignas(16) vec {
-                        T x[V];
-                    };
-                    #pragma unroll
-                    for (int j0 = 0; j0 < CPT; j0 += V) {
-                        const int c0 = ch * CPT + j0;
-                        const vec scj = *reinterpret_cast<const vec *>(s_col + 3 * NH + c0);
-                        const vec vj = *reinterpret_cast<const vec *>(s_col + 1 * NH + c0);
-                        vec sqj{}, qj{};
-                        if constexpr (KERNEL == K_RBF) { sqj = *reinterpret_cast<const vec *>(s_col + 2 * NH + c0); }
-                        if constexpr (MODE == MODE_SYM) { qj = *reinterpret_cast<const vec *>(s_col + 0 * NH + c0); }
-                        #pragma unroll
-                        for (int u = 0; u < V; ++u) {
-                            const int j = j0 + u;
-                            const T dot = a[j] * (sci * scj.x[u]);
-                            const T kv = kernel_from_dot<KERNEL, T, DEG>(dot, sqi, sqj.x[u], p.kp);
-                            T t = kv;
-                            if constexpr (MODE == MODE_SYM) {
-                                t = kv + qa - qi - qj.x[u];
-                                if constexpr (DIAG) {
-                                    if (row == h * NH + c0 + u) { t += p.cost_inv; }
-                                }
-                            }
-                            rowacc = pb_fma(t, vj.x[u], rowacc);
-                            a[j] = t * vi;  // mirrored contribution of this row to column c0 + u
-                        }
-                    }
-                };
-                auto phase2_deg = [&](auto deg_tag) {
-                    if (diag) {
-                        phase2(deg_tag, std::true_type{});
-                    } else {
-                        phase2(deg_tag, std::false_type{});
-                    }
-                };
-                if constexpr (KERNEL == K_POLYNOMIAL) {
-                    switch (p.kp.degree) {  // CTA-uniform
-                        case 2: phase2_deg(std::integral_constant<int, 2>{}); break;
-                        case 3: phase2_deg(std::integral_constant<int, 3>{}); break;
-                        default: phase2_deg(std::integral_constant<int, 0>{}); break;
-                    }
-                } else {
-                    phase2_deg(std::integral_constant<int, 0>{});
-                }
-                if constexpr (MODE == MODE_SYM) {
-                    if (!diag) {  // CTA-uniform
-                        // butterfly per 32 columns: after 5 halving steps lane c holds the sum over the warp's 32 rows of column c
-                        #pragma unroll
-                        for (int cc = 0; cc < CPT / 32; ++cc) {
-                            #pragma unroll
-                            for (int step = 16; step >= 1; step >>= 1) {
-                                const bool upper = (lane & step) != 0;
-                                #pragma unroll
-                                for (int k = 0; k < step; ++k) {
-                                    const T send = upper ? a[cc * 32 + k] : a[cc * 32 + k + step];
-                                    const T keep = upper ? a[cc * 32 + k + step] : a[cc * 32 + k];
-                                    a[cc * 32 + k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-                                }
-                            }
-                            s_colsum[quarter * NH + ch * CPT + cc * 32 + lane] = a[cc * 32];
-                        }
-                    }
-                }
-                if (h == UNITS - 1 && ch == 1) { s_rowsum[row] = rowacc; }
-                named_bar_sync(1, I8_EPI_THREADS);  // column sums of the four row quarters / row sums of the second column half visible
-                if constexpr (MODE == MODE_SYM) {
-                    if (!diag && valid && et < NH) {
-                        const T s = ((s_colsum[et] + s_colsum[NH + et]) + s_colsum[2 * NH + et]) + s_colsum[3 * NH + et];
-                        const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
-                        p.partial[mslot * TILE + h * NH + et] = (col0 + et < p.n_cols) ? s : T(0);
-                    }
-                }
-                if (h == UNITS - 1 && ch == 0 && valid) {
-                    const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
-                    p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : T(0);
-                }
-                named_bar_sync(1, I8_EPI_THREADS);  // s_col / s_colsum / s_rowsum consumed before the next unit overwrites them
+                i8_epilogue_unit<T, S, KERNEL, MODE, false>(p, s_row, s_col, s_colsum, s_rowsum, tmem_base, tfull, tempty, unit_iter, I, J, h, valid, diag, qa, rowacc);
             }
         }
     }

@@ -101,7 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(I8_THREADS, 1)
 tile_kernel_i8_pair(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR1, const __grid_constant__ CUtensorMap tmBig,
                     const __grid_constant__ CUtensorMap tmSmall, const TileParams<T> p) {
     using L8 = I8PairLayout2<T, S_>;
-    constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, CPT = L8::CPT, SPM = L8::SPM;
+    constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES, SPM = L8::SPM;
     extern __shared__ unsigned char smem_raw[];
     if (p.done != nullptr && *p.done != 0) { return; }
 
@@ -291,17 +291,12 @@ tile_kernel_i8_pair(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ===== epilogue (both CTAs): warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns CPT ch .. + CPT - 1 of the unit =====
-        // (identical to tile_kernel_i8's except for the work decomposition and the remote hand-back of TMEM)
-        const int quarter = warp & 3;
-        const int ch = (warp - 2) >> 2;        // column half of the unit
-        const int row = quarter * 32 + lane;   // accumulator row of this thread
-        const int et = tid - 64;               // 0..255 among the epilogue threads
+        // ===== epilogue (both CTAs): warps 2..9, the unit epilogue of tile_i8.cuh with the remote hand-back of TMEM =====
         std::uint32_t unit_iter = 0;
         for (std::uint64_t L = p.tile_lo + cluster_id; L < p.tile_hi; L += num_clusters) {
             std::uint32_t I2, J2;
             decode2(L, I2, J2);
-            const std::uint32_t I = 2 * I2 + rank, row0 = I * TILE;
+            const std::uint32_t I = 2 * I2 + rank;
             const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
             for (std::uint32_t c = 0; c < 2; ++c) {
                 const std::uint32_t J = 2 * J2 + c;
@@ -310,165 +305,7 @@ tile_kernel_i8_pair(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bool diag = (MODE == MODE_SYM) && (I == J);
                 T rowacc = T(0);
                 for (int h = 0; h < UNITS; ++h, ++unit_iter) {
-                    const std::uint32_t col0 = J * TILE + h * NH;
-                    if (h == 0 && et < TILE) {
-                        const std::uint32_t gi = row0 + et;
-                        const bool oki = gi < p.n_rows;
-                        s_row[0 * TILE + et] = (MODE == MODE_SYM && oki) ? p.q[gi] : T(0);
-                        s_row[1 * TILE + et] = (MODE == MODE_SYM && oki) ? p.v[gi] : T(0);
-                        s_row[2 * TILE + et] = (KERNEL == K_RBF && oki) ? p.row_sq[gi] : T(0);
-                        s_row[3 * TILE + et] = oki ? p.A_scale[gi] : T(0);
-                    }
-                    if (et >= TILE && et < TILE + NH) {
-                        const int cidx = et - TILE;
-                        const std::uint32_t gj = col0 + cidx;
-                        const bool okj = gj < p.n_cols;
-                        s_col[0 * NH + cidx] = (MODE == MODE_SYM && okj) ? p.q[gj] : T(0);
-                        s_col[1 * NH + cidx] = okj ? p.v[gj] : T(0);
-                        s_col[2 * NH + cidx] = (KERNEL == K_RBF && okj) ? p.col_sq[gj] : T(0);
-                        s_col[3 * NH + cidx] = okj ? p.B_scale[gj] : T(0);
-                    }
-                    named_bar_sync(1, I8_EPI_THREADS);
-                    const T qi = s_row[0 * TILE + row], vi = s_row[1 * TILE + row], sqi = s_row[2 * TILE + row];
-                    const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;  // see tile_kernel_i8
-                    const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
-
-                    const long long c2 = (p.stats != nullptr && tid == 64) ? clock64() : 0;
-                    mbar_wait(tfull, unit_iter & 1u);
-                    if (p.stats != nullptr && tid == 64) { atomicAdd(p.stats + blockIdx.x * 8 + 4, static_cast<unsigned long long>(clock64() - c2)); }
-                    tcgen05_fence_after();
-                    const std::uint32_t taddr = tmem_base + (static_cast<std::uint32_t>(quarter * 32) << 16) + static_cast<std::uint32_t>(ch * CPT);
-
-                    // phase 1: S int32 diagonals -> one value per element (Horner in fp64 from the least significant diagonal)
-                    T a[CPT];
-                    bool released = false;
-                    if constexpr (sizeof(T) == 4 && S == 3 && CPT == 64) {
-                        if (fold3 && p.slow_drain == 0) {
-                            // fp32 fast drain: raw diagonals into registers, folded to two words per element, TMEM released before any floating-point work
-                            std::uint32_t hi[CPT], lo[CPT];
-                            #pragma unroll
-                            for (int half = 0; half < 2; ++half) {
-                                std::uint32_t r0[32], r1[32], r2[32];
-                                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(0 * NH + half * 32), r0);
-                                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(1 * NH + half * 32), r1);
-                                tmem_ld_32x32b_x32_nowait(taddr + static_cast<std::uint32_t>(2 * NH + half * 32), r2);
-                                tmem_ld_wait();
-                                #pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    hi[half * 32 + j] = r2[j] * 256u + r1[j];
-                                    lo[half * 32 + j] = r0[j];
-                                }
-                            }
-                            tcgen05_fence_before();
-                            __syncwarp();
-                            if (lane == 0) { mbar_arrive_cluster(tempty, 0u); }
-                            released = true;
-                            #pragma unroll
-                            for (int j = 0; j < CPT; ++j) { a[j] = static_cast<T>(fma(i32_to_f64(lo[j]), 0.00390625, i32_to_f64(hi[j]))); }
-                        }
-                    }
-                    if (!released) {
-                        #pragma unroll
-                        for (int g = 0; g < CPT / 8; ++g) {
-                            std::uint32_t r[S][8];
-                            #pragma unroll
-                            for (int t = 0; t < S; ++t) { tmem_ld_32x32b_x8(taddr + static_cast<std::uint32_t>(t * NH + g * 8), r[t]); }
-                            tmem_ld_wait();
-                            #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                double s = i32_to_f64(r[0][j]);
-                                #pragma unroll
-                                for (int t = 1; t < S; ++t) { s = fma(s, 0.00390625, i32_to_f64(r[t][j])); }
-                                a[g * 8 + j] = static_cast<T>(s);
-                            }
-                        }
-                        // all of this warp's accumulator reads are done: hand TMEM back to the leader's MMA warp
-                        tcgen05_fence_before();
-                        __syncwarp();
-                        if (lane == 0) { mbar_arrive_cluster(tempty, 0u); }
-                    }
-
-                    // phase 2: kernel function and the weighted sums (same instantiation scheme, operation order and rounding as tile_kernel_i8)
-                    auto phase2 = [&](auto deg_tag, auto diag_tag) {
-                        constexpr int DEG = decltype(deg_tag)::value;
-                        constexpr bool DIAG = decltype(diag_tag)::value;
-                        constexpr int V = 16 / static_cast<int>(sizeof(T));
-                        struct alignas(16) vec {
-                            T x[V];
-                        };
-                        #pragma unroll
-                        for (int j0 = 0; j0 < CPT; j0 += V) {
-                            const int c0 = ch * CPT + j0;
-                            const vec scj = *reinterpret_cast<const vec *>(s_col + 3 * NH + c0);
-                            const vec vj = *reinterpret_cast<const vec *>(s_col + 1 * NH + c0);
-                            vec sqj{}, qj{};
-                            if constexpr (KERNEL == K_RBF) { sqj = *reinterpret_cast<const vec *>(s_col + 2 * NH + c0); }
-                            if constexpr (MODE == MODE_SYM) { qj = *reinterpret_cast<const vec *>(s_col + 0 * NH + c0); }
-                            #pragma unroll
-                            for (int u = 0; u < V; ++u) {
-                                const int j = j0 + u;
-                                const T dot = a[j] * (sci * scj.x[u]);
-                                const T kv = kernel_from_dot<KERNEL, T, DEG>(dot, sqi, sqj.x[u], p.kp);
-                                T t = kv;
-                                if constexpr (MODE == MODE_SYM) {
-                                    t = kv + qa - qi - qj.x[u];
-                                    if constexpr (DIAG) {
-                                        if (row == h * NH + c0 + u) { t += p.cost_inv; }
-                                    }
-                                }
-                                rowacc = pb_fma(t, vj.x[u], rowacc);
-                                a[j] = t * vi;  // mirrored contribution of this row to column c0 + u
-                            }
-                        }
-                    };
-                    auto phase2_deg = [&](auto deg_tag) {
-                        if (diag) {
-                            phase2(deg_tag, std::true_type{});
-                        } else {
-                            phase2(deg_tag, std::false_type{});
-                        }
-                    };
-                    if constexpr (KERNEL == K_POLYNOMIAL) {
-                        switch (p.kp.degree) {  // CTA-uniform
-                            case 2: phase2_deg(std::integral_constant<int, 2>{}); break;
-                            case 3: phase2_deg(std::integral_constant<int, 3>{}); break;
-                            default: phase2_deg(std::integral_constant<int, 0>{}); break;
-                        }
-                    } else {
-                        phase2_deg(std::integral_constant<int, 0>{});
-                    }
-                    if constexpr (MODE == MODE_SYM) {
-                        if (!diag) {  // CTA-uniform
-                            #pragma unroll
-                            for (int cc = 0; cc < CPT / 32; ++cc) {
-                                #pragma unroll
-                                for (int step = 16; step >= 1; step >>= 1) {
-                                    const bool upper = (lane & step) != 0;
-                                    #pragma unroll
-                                    for (int k = 0; k < step; ++k) {
-                                        const T send = upper ? a[cc * 32 + k] : a[cc * 32 + k + step];
-                                        const T keep = upper ? a[cc * 32 + k + step] : a[cc * 32 + k];
-                                        a[cc * 32 + k] = keep + __shfl_xor_sync(0xffffffffu, send, step);
-                                    }
-                                }
-                                s_colsum[quarter * NH + ch * CPT + cc * 32 + lane] = a[cc * 32];
-                            }
-                        }
-                    }
-                    if (h == UNITS - 1 && ch == 1) { s_rowsum[row] = rowacc; }
-                    named_bar_sync(1, I8_EPI_THREADS);
-                    if constexpr (MODE == MODE_SYM) {
-                        if (!diag && valid && et < NH) {
-                            const T s = ((s_colsum[et] + s_colsum[NH + et]) + s_colsum[2 * NH + et]) + s_colsum[3 * NH + et];
-                            const std::size_t mslot = static_cast<std::size_t>(J) * p.T_cols + I;
-                            p.partial[mslot * TILE + h * NH + et] = (col0 + et < p.n_cols) ? s : T(0);
-                        }
-                    }
-                    if (h == UNITS - 1 && ch == 0 && valid) {
-                        const std::size_t slot = static_cast<std::size_t>(I) * p.T_cols + J;
-                        p.partial[slot * TILE + row] = (row0 + row < p.n_rows) ? rowacc + s_rowsum[row] : T(0);
-                    }
-                    named_bar_sync(1, I8_EPI_THREADS);
+                    i8_epilogue_unit<T, S, KERNEL, MODE, true>(p, s_row, s_col, s_colsum, s_rowsum, tmem_base, tfull, tempty, unit_iter, I, J, h, valid, diag, qa, rowacc);
                 }
             }
         }

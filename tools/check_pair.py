@@ -23,7 +23,7 @@ quick = "--quick" in sys.argv
 only = [a.split("=")[1] for a in sys.argv if a.startswith("--only=")]  # --only=C2 / --only=C3: one real type
 dtypes = {"C2": (np.float64,), "C3": (np.float32,)}[only[0]] if only else (np.float64, np.float32)
 bad = 0
-for dtype in dtypes:
+for dtype in (() if "--skip-parity" in sys.argv else dtypes):
     for (N, d) in ((2, 3), (130, 1), (257, 40), (386, 65), (1000, 96), (2049, 333), (700, 1200), (5000, 129)):
         for kernel in ("linear", "polynomial", "rbf"):
             X, y = make_data(N, d, 7, dtype)
@@ -69,7 +69,9 @@ for dtype in dtypes:
     bad += 0 if same else 1
     print(f"{np.dtype(dtype).name} solve rbf 1500x128: iterations {res[A]['iterations']} / {res[B]['iterations']}  alpha identical {same}", flush=True)
 print("PARITY", "OK" if bad == 0 else f"FAIL ({bad} cases)", flush=True)
-if bad != 0 or "--no-time" in sys.argv:
+if "--skip-parity" in sys.argv:
+    pass
+elif bad != 0 or "--no-time" in sys.argv:
     sys.exit(1 if bad else 0)
 
 shapes = [("C2", 16384, 4096), ("C3", 32768, 1024)] if quick else [("C2", 16384, 4096), ("C2", 65536, 4096), ("C3", 32768, 1024), ("C3", 131072, 1024)]
@@ -77,11 +79,12 @@ for workload, rows, feats in shapes:
     if only and workload != only[0]:
         continue
     _, _, kernel, dtype, _ = WORKLOADS[workload]
+    kernel = ([a.split("=")[1] for a in sys.argv if a.startswith("--kernel=")] or [kernel])[0]  # --kernel=linear: the same shape with another kernel function
     X, _ = make_device_data(rows, feats, dtype, 7, dev)
     ds = be.dataset(X)
     q, k_last = be.run_q_kernel(ds, kernel)
     v = np.random.default_rng(1).uniform(1, 2, rows - 1).astype(np.dtype(dtype))
-    out = {"workload": workload, "rows": rows, "features": feats}
+    out = {"workload": workload, "rows": rows, "features": feats, "kernel": kernel}
     res = {}
     reps = 3 if rows <= 32768 else 6
     for impl in (A, B, A, B):
@@ -95,7 +98,7 @@ for workload, rows, feats in shapes:
     out["bit_identical"] = bool(np.array_equal(res[A], res[B]))
     print(json.dumps(out), flush=True)
     if "--stats" in sys.argv:
-        be.set_option("tile_stats", 1)
+        be.set_option("tile_stats", 2)
         for impl in (A, B):
             be.set_option("impl", impl)
             be.run_svm_kernel(ds, q, v, np.zeros_like(v), float(k_last) + 1.0, 1.0, 1.0, kernel)

@@ -12,8 +12,9 @@ import plssvm_b200 as pb  # noqa: E402
 from datagen import make_data  # noqa: E402
 
 be = pb.Backend(0)
-# the default library holds impl 1 / 2 / 6 / 7; the variants 4 / 5 / 8 / 9 only exist in a build with -DPLSSVM_B200_EXPERIMENTAL
-impls = {np.float64: (1, 2, 6, 8), np.float32: (1, 2, 4, 5, 6, 7, 8, 9)} if pb.has_experimental() else {np.float64: (1, 2, 6), np.float32: (1, 2, 6, 7)}
+# the default library holds impl 1 / 2 / 6 / 7 and, for fp32, 10 (CTA pairs); the variants 4 / 5 / 8 / 9 and the fp64 CTA-pair kernel only exist in a build
+# with -DPLSSVM_B200_EXPERIMENTAL
+impls = {np.float64: (1, 2, 6, 8, 10), np.float32: (1, 2, 4, 5, 6, 7, 8, 9, 10)} if pb.has_experimental() else {np.float64: (1, 2, 6), np.float32: (1, 2, 6, 7, 10)}
 for dtype in (np.float64, np.float32):
     X, y = make_data(301, 37, 1, dtype)
     P, _ = make_data(150, 37, 2, dtype)
