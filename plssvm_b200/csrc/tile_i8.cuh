@@ -359,7 +359,7 @@ __device__ __forceinline__ void i8_epilogue_unit(const TileParams<T> &p, T *s_ro
     // fp32, S = 3, d <= 1984: the two upper diagonals fit one int32 (|ACC_2| 2^8 + |ACC_1| <= d (2^20 + 2^14) < 2^31), so an element is two
     // words (fast drain below) and its recombination one IMAD + 3 instead of 5 fp64 operations; the sum is 256 x the value, folded
     // into the row scale.  Both forms are exact in fp64: bit-identical results.
-    const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u;
+    const bool fold3 = sizeof(T) == 4 && S == 3 && p.ld8 <= 1984u && p.slow_drain == 0;
     const T sci = fold3 ? s_row[3 * TILE + row] * T(0.00390625) : s_row[3 * TILE + row];
 
     stamp(-1, 7);  // vector loads + named barrier before the wait
@@ -375,7 +375,7 @@ __device__ __forceinline__ void i8_epilogue_unit(const TileParams<T> &p, T *s_ro
     T a[CPT];
     bool released = false;
     if constexpr (sizeof(T) == 4 && S == 3 && CPT == 64) {
-        if (fold3 && p.slow_drain == 0) {
+        if (fold3) {
             // fp32 fast drain (measured with tools/tmem_probe: the fp64 -> fp32 conversion runs at ~12 elements / clk / SM and a
             // tcgen05.ld + wait round trip costs a few hundred cycles, so converting while the accumulators are still held kept the
             // tensor pipe idle for ~1/3 of a d = 1024 unit).  Here the raw int32 diagonals of all 64 columns are pulled into
