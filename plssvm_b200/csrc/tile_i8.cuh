@@ -48,6 +48,11 @@
 #ifndef PB_ELECT_MMA
     #define PB_ELECT_MMA -1
 #endif
+// how the B planes of one A plane are split into N <= 256 instructions (see the MMA issuer): 1 = as evenly as possible (measured + 0.6 % at C2 on one
+// box, bit-identical: profiles/r02/ab_pair_kernel.txt), 0 = greedily
+#ifndef PB_I8_EVEN_CHUNKS
+    #define PB_I8_EVEN_CHUNKS 1
+#endif
 
 namespace pb {
 
@@ -686,11 +691,16 @@ tile_kernel_i8(const TileParams<T> p) {
                             #pragma unroll
                             for (int pp = S - 1; pp >= 0; --pp) {
                                 const int q_lo = S - 1 - pp, cnt = pp + 1;
+                                // the cnt planes go into ceil(cnt / SLICES_PER_MMA) instructions: PB_I8_EVEN_CHUNKS = 0 fills them greedily (fp64: 4 + 3, 4 + 2, 4 + 1),
+                                // 1 splits them as evenly as possible (4 + 3, 3 + 3, 3 + 2: no N = 64 instruction — the shape that starves on the shared-memory port — next to a full one)
+                                constexpr int SPM = L8::SLICES_PER_MMA;
+                                const int nchunks = (cnt + SPM - 1) / SPM, base_sz = PB_I8_EVEN_CHUNKS ? cnt / nchunks : SPM, rem = PB_I8_EVEN_CHUNKS ? cnt % nchunks : 0;
                                 #pragma unroll
-                                for (int c = 0; L8::SLICES_PER_MMA * c < cnt; ++c) {
-                                    const int nsl = cnt - L8::SLICES_PER_MMA * c < L8::SLICES_PER_MMA ? cnt - L8::SLICES_PER_MMA * c : L8::SLICES_PER_MMA;
-                                    const std::uint32_t d_acc = tmem_base + static_cast<std::uint32_t>(c * L8::SLICES_PER_MMA * NH);
-                                    const std::uint64_t bdesc = d_b + koff + static_cast<std::uint64_t>(((q_lo + L8::SLICES_PER_MMA * c) * L8::B_SLICE) >> 4);
+                                for (int c = 0; c < nchunks; ++c) {
+                                    const int start = c * base_sz + (c < rem ? c : rem);
+                                    const int nsl = PB_I8_EVEN_CHUNKS ? base_sz + (c < rem ? 1 : 0) : (cnt - start < SPM ? cnt - start : SPM);
+                                    const std::uint32_t d_acc = tmem_base + static_cast<std::uint32_t>(start * NH);
+                                    const std::uint64_t bdesc = d_b + koff + static_cast<std::uint64_t>(((q_lo + start) * L8::B_SLICE) >> 4);
                                     const std::uint32_t idesc = i8_idesc(static_cast<std::uint32_t>(nsl * NH)), acc = (first && pp == S - 1) ? 0u : 1u;
                                     if (a_tmem && pp >= 4) {  // (compile-time after unrolling)
                                         umma_i8_ts(d_acc, a_buf + static_cast<std::uint32_t>((pp - 4) * 8), bdesc, idesc, acc);
