@@ -618,7 +618,7 @@ def run_ours(args):
         "metric": "cg_matvec_tflops", "value": m["value"], "unit": "TFLOP/s", "n_gpus": rk.n_gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64" if dtype == "float64" else "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}" + ("" if headline else f" [DEV OVERRIDE rows={N} features={d}]") + (" [factorised linear fast path]" if args.linear_factorized else ""),
-                   "kernel": kernel, "rows": N, "features": d, "flops_per_step": F, "l2": "inputs (2.1 GB) larger than L2; no flush needed",
+                   "kernel": kernel, "rows": N, "features": d, "flops_per_step": F, "l2": f"inputs ({N * d * (8 if dtype == 'float64' else 4) / 1e9:.1f} GB of X, {N * d * (7 if dtype == 'float64' else 3) / 1e9:.1f} GB of digit planes) larger than the 126 MB L2; no flush needed",
                    "parallelism": f"triangle tiles sharded over {rk.n_gpus} GPU(s) ({'one process, device group behind the C ABI' if rk.group else 'one process per GPU' if rk.world > 1 else 'single GPU'}), "
                                   f"X replicated, {'rate-weighted' if args.balance and rk.n_gpus > 1 else 'equal'} tile shares"},
         "cg_iters_per_s": args.steps / (m["dev_ms"] * 1e-3), "wall_ms_per_step": m["wall"] / args.steps * 1e3,

@@ -64,6 +64,10 @@ constexpr int I8_BK = 64;                                  // bytes (= features)
 #ifndef PB_I8_BK_F32
     #define PB_I8_BK_F32 64
 #endif
+// the same for the fp64 kernel (64: 2 x 84 KB stages; 32: 5 x 42 KB)
+#ifndef PB_I8_BK_F64
+    #define PB_I8_BK_F64 64
+#endif
 constexpr int I8_THREADS = 320;                            // producer warp, MMA warp, 8 epilogue warps
 constexpr int I8_EPI_THREADS = 256;
 constexpr std::uint32_t I8_TMEM_COLS = 512;
@@ -78,7 +82,7 @@ template <typename T>
 struct I8;
 template <>
 struct I8<double> {
-    static constexpr int S = 7, S_EXACT = 7, NH = 64, AUTO_RANGE = 20, BK = I8_BK;
+    static constexpr int S = 7, S_EXACT = 7, NH = 64, AUTO_RANGE = 20, BK = PB_I8_BK_F64;
 };
 template <>
 struct I8<float> {
