@@ -1,20 +1,25 @@
-// int8-slice tile kernel on CTA pairs WITH the wide-N instructions: tcgen05.mma.cta_group::2.kind::i8, M = 256 (two SMs x 128 rows), N <= 256.
+// int8-slice tile kernel on CTA pairs: tcgen05.mma.cta_group::2.kind::i8, M = 256 (two SMs x 128 rows), N <= 256.  The automatic choice for fp32.
 //
-// Same arithmetic, accumulator layout and epilogue as tile_i8.cuh (results are bit-identical); what changes is how the B operand reaches the
-// tensor cores.  The single-CTA kernel is bound by the shared-memory port of its SM: per 32-feature step the MMAs read
-// 96 KB (fp64) / 40 KB (fp32) of operands and the producer writes 42 / 24 KB into the ring — 154 / 171 B/clk at the tensor pipe's pace against
-// the 128 B/clk the port delivers.  With cta_group::2 the two tensor cores of a pair share the B operand: each CTA supplies only HALF of the N
-// rows of every instruction out of its own shared memory, so the B reads per SM halve (68 / 28 KB of operand reads per step).
+// Same arithmetic, accumulator layout and unit epilogue (i8_epilogue_unit) as tile_i8.cuh — results are bit-identical; what changes is how the B
+// operand reaches the tensor cores.  On a single CTA the MMAs of a 32-feature step read 96 KB (fp64) / 40 KB (fp32) of operands and the producer
+// writes 42 / 24 KB into the ring: 154 / 171 B/clk at the tensor pipe's pace against the 128 B/clk of the shared-memory port.  With
+// cta_group::2 the two tensor cores of a pair share the B operand: each CTA supplies only HALF of the N rows of every instruction out of its own
+// shared memory (ncu at C3: tensor-core shared-memory wavefronts 61 % -> 57 % with the tensor pipe 74 % -> 76 % active).
 //
-// The wide-N trick (one instruction multiplies A_p with several consecutive B planes that lie side by side in shared memory) needs the B rows
-// of an instruction to be [first half | second half] = [CTA 0 | CTA 1] of the CONCATENATION of its planes, at the SAME shared-memory offset in
-// both CTAs (one descriptor serves the pair).  Layout of a stage's B area that achieves this for every instruction of a step:
-//   * region 1, plane-sized slots j = 0 .. S - HALF - 1 (HALF = half the planes of a full N = 256 instruction): CTA 0 holds plane j, CTA 1 plane
-//     j + HALF.  A full instruction over planes q .. q + 2 HALF - 1 points at slot q: CTA 0 supplies planes q .. q + HALF - 1, CTA 1 the rest.
-//   * region 2, one piece per partial instruction (the nsl < 2 HALF planes S - nsl .. S - 1 that end a plane's range): CTA r holds the rows
-//     [r nsl NH / 2, (r + 1) nsl NH / 2) of that concatenation.
-// fp64 (S = 7, NH = 64): 5 planes + 192 rows = 32 KB of B per slab and CTA (single-CTA kernel: 28 KB) -> 110 KB through the port per step
-// = 123 B/clk; fp32 (S = 3, NH = 128): 2 planes + 64 rows = 20 KB (24 KB) -> 50 KB per step = 130 B/clk.
+// Two forms of the B area of a ring stage (compile-time per real type, I8PairConfig):
+//   * NARROW (the fp32 default): one instruction per plane pair, N = NH; CTA r stages only ITS NH / 2 rows of every B plane — the fewest bytes
+//     (fp32: 36 KB instead of 48 KB per slab and CTA, 6 stages), but S (S + 1) / 2 instructions that each re-read an A plane.
+//   * WIDE: the wide-N instructions of tile_i8.cuh (one instruction multiplies A_p with several consecutive B planes that lie side by side in
+//     shared memory).  One descriptor serves the pair, so the B rows of an instruction must be [first half | second half] = [CTA 0 | CTA 1] of the
+//     CONCATENATION of its planes at the SAME shared-memory offset in both CTAs:
+//       - region 1, plane-sized slots j = 0 .. S - HALF - 1 (HALF = half the planes of a full N = 256 instruction): CTA 0 holds plane j, CTA 1
+//         plane j + HALF.  A full instruction over planes q .. q + 2 HALF - 1 points at slot q: CTA 0 supplies planes q .. q + HALF - 1, CTA 1 the rest.
+//       - region 2, one piece per partial instruction (the nsl < 2 HALF planes S - nsl .. S - 1 that end a plane's range): CTA r holds the rows
+//         [r nsl NH / 2, (r + 1) nsl NH / 2) of that concatenation.
+//     fp64 (S = 7, NH = 64): 5 planes + 192 rows = 32 KB of B per 64-feature slab and CTA (single CTA: 28 KB), 123 B/clk through the port.
+// Measured (profiles/r02/ab_pair_kernel.txt): fp32 narrow + 4.5 % at C3 (wide + 3.5 %); fp64 wide - 15 % at C2 (the fp64 epilogues of a pair run
+// their exp chains in lock step and become the bottleneck, and the N = 64 / 128 / 192 / 256 mix of cta_group::2 instructions issues ~10 % slower
+// than on single CTAs): the fp64 instantiation is only built with -DPLSSVM_B200_EXPERIMENTAL.
 //   * both CTAs: warp 0 = TMA producer — the pre-swizzled boxes of split_i8_kernel are contiguous, so every piece is one 2-D box of 128-byte lines
 //     (cp.async.bulk.tensor ... cta_group::2, completing on the LEADER's mbarrier); warps 2-9 = epilogue over their own 128 accumulator rows
 //   * leader CTA (cluster rank 0): warp 1 issues the MMAs for the pair; tcgen05.commit ... multicast::cluster releases the ring stage /

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Hardware check of the CTA-pair wide-N int8-slice kernel (impl 10, tile_i8_pair.cuh) against the single-CTA kernel (impl 6):
 bit-identity of matvec / predict results over ragged shapes for both real types, then tile-kernel time A/B on the bench shapes.
-    python tools/check_pair.py [--quick] [--no-time]"""
+    python tools/check_pair.py [--quick] [--no-time] [--skip-parity] [--only=C2|C3] [--kernel=linear|polynomial|rbf] [--stats]
+(fp64 runs the pair kernel only in a library built with PLSSVM_B200_EXPERIMENTAL=1, otherwise impl 10 resolves to 6; PLSSVM_B200_LIB selects the library:
+A/B of two builds on one box.  --stats prints the per-role wait fractions; with a -DPB_TILE_STATS_FINE build also the split of the epilogue's time.)"""
 import json
 import os
 import sys
