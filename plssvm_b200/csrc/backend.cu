@@ -459,7 +459,7 @@ int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0, con
     if (ctx->impl != 0) { return ctx->impl; }
     // auto: int8 slices on tcgen05 where the int32 accumulators cannot overflow (fp32 with at least one 256-row block of the A operand: on CTA
     // pairs); callers fall back to 2 for badly scaled rows: fp64 -> TMA + DMMA (tile_dmma.cuh), fp32 -> TMA + tcgen05 3xTF32 + TMEM (tile_tf32.cuh)
-    if (features > 0 && features <= pb::I8_MAX_FEATURES) { return (sizeof(T) == 4 && ctx->fp32_pair != 0 && rows >= 2 * TILE && ctx->num_sms >= 2) ? 10 : 6; }
+    if (features > 0 && features <= pb::I8_MAX_FEATURES) { return (sizeof(T) == 4 && ctx->fp32_pair != 0 && rows >= 2 * TILE && ctx->pairs_ok != 0) ? 10 : 6; }
     return 2;
 }
 // automatic kernel choice only: the int8-slice tiles are used unless an operand holds badly scaled rows (split_i8_kernel)
@@ -1450,6 +1450,9 @@ plssvm_b200_ctx *create_device_context(const int device) {
     auto ctx = std::make_unique<plssvm_b200_ctx>();
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    int cluster_launch = 0;  // CTA pairs need thread-block clusters and two SMs; without them the automatic choice stays on single CTAs
+    PB_CUDA(cudaDeviceGetAttribute(&cluster_launch, cudaDevAttrClusterLaunch, device));
+    ctx->pairs_ok = (cluster_launch != 0 && ctx->num_sms >= 2) ? 1 : 0;
     ctx->leader = ctx.get();
     PB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PB_CUDA(cudaEventCreate(&ctx->ev_loop0));

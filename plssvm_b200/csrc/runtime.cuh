@@ -161,6 +161,7 @@ struct plssvm_b200_dataset;
 struct plssvm_b200_ctx {
     int device = 0;
     int num_sms = 0;
+    int pairs_ok = 0;  // device can launch 2-CTA clusters (the CTA-pair int8-slice kernel)
     cudaStream_t stream = nullptr;
     int rank = 0, world = 1;
     pbrt::nccl_api::comm_t comm = nullptr;
