@@ -511,7 +511,10 @@ def extra_workloads(rk, be, args):
         X, y = make_host_data(N, d, dtype, 42)
         t0 = time.perf_counter()
         r = be.solve(X, y, kernel, eps=1e-8)
-        gpu_s = time.perf_counter() - t0
+        gpu_s = time.perf_counter() - t0  # the FIRST linear-kernel call of this context: includes loading the kernels and growing the workspaces
+        t0 = time.perf_counter()
+        be.solve(X, y, kernel, eps=1e-8)
+        gpu_repeat_s = time.perf_counter() - t0
         t = be.timings()
         orc = oracle.Oracle("reference" if oracle.available("reference") else "port")
         orc.set_threads(len(os.sched_getaffinity(0)))
@@ -520,7 +523,7 @@ def extra_workloads(rk, be, args):
         cpu_s = time.perf_counter() - t0
         same = r["iterations"] == rc["iterations"]
         return {"workload": f"C1: {desc}, whole fit to eps = 1e-8 through plssvm_b200_solve_f64 (host buffers) vs the reference's OpenMP path", "metric": "fit_seconds", "value": gpu_s,
-                "unit": "s", "higher_is_better": False, "iterations": r["iterations"], "cpu_seconds": cpu_s, "cpu_iterations": rc["iterations"], "cpu_threads": orc.max_threads(),
+                "unit": "s", "higher_is_better": False, "repeat_call_seconds": gpu_repeat_s, "cg_loop_ms": t["cg_loop_ms"], "iterations": r["iterations"], "cpu_seconds": cpu_s, "cpu_iterations": rc["iterations"], "cpu_threads": orc.max_threads(),
                 "cpu_kind": orc.reported_kind(), "speedup_vs_cpu": cpu_s / gpu_s, "tile_impl": int(t["impl_used"]), "gpu_launches": int(t["kernel_launches"]),
                 "alpha_max_rel_diff_vs_cpu": float(np.max(np.abs(r["alpha"] - rc["alpha"])) / np.max(np.abs(rc["alpha"]))) if same else None,
                 "matvec_tflops_incl_setup": matvec_flops(N, d) * t["matvec_calls"] / (t["matvec_ms"] * 1e-3) / 1e12 if t["matvec_ms"] > 0 else None}
