@@ -103,7 +103,8 @@ const char *plssvm_b200_last_error(void);
  * re-cut the tile shares every "balance_interval" (default 8) iterations in proportion to the tile-kernel rates the ranks
  * measured — GPUs under a power cap do not run at the same clock; 0 = fixed equal shares, bit-reproducible run to run),
  * "shard_upload" (0/1, default 1; several devices / ranks: each uploads 1 / world of the rows, NCCL all-gather);
- * "tile_stats" (0/1, profiling: per-role wait-cycle counters of the int8-slice tile kernel, see plssvm_b200_timings), "fp32_fast_drain" (0/1,
+ * "tile_stats" (0/1, profiling: per-role wait-cycle counters of the int8-slice tile kernel, see plssvm_b200_timings; 2 = additionally, in a library built
+ * with -DPB_TILE_STATS_FINE, one JSON line per tile launch on stderr with the split of the epilogue's time), "fp32_fast_drain" (0/1,
  * default 1; A/B switch of the fp32 epilogue: release TMEM before / after the fp64 -> fp32 conversion, bit-identical results),
  * "fp32_pair" (0/1, default 1; automatic kernel choice for fp32: the int8-slice tiles run on CTA pairs (impl 10: tcgen05.mma.cta_group::2, the two
  * tensor cores of a pair share the B operand) instead of single CTAs (impl 6) — bit-identical results, measured 4 - 5 % faster at C3),
