@@ -226,11 +226,11 @@ def tile_roofline(impl_used, dtype, kernel, mode, achieved, avg_launch_ms, launc
     fp_pipe = float(pk.get("dmma_tflops_sustained_3s", 37.0)) if f64 else float(pk.get("cublas_sgemm_tf32_random_tflops_sustained_4s", 770.0)) / 3.0
     out = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "avg_launch_ms": avg_launch_ms, "launches_timed": int(launches), "flops_per_launch": flops_per_launch,
            "traffic": traffic}
-    if impl_used in (6, 7, 8, 9, 10):
+    if impl_used in (6, 7, 8, 9, 10, 11):
         products = 28.0 if f64 else (10.0 if impl_used == 7 else 6.0)
         planes = 7 if f64 else (4 if impl_used == 7 else 3)
         sus, burst = float(pk.get("i8_mma_n256_random_tops_sustained_3s", 3819.0)) / products, float(pk.get("i8_mma_n256_random_tops_burst", 4425.0)) / products
-        variant = {8: ", 2 x 2 CTA clusters + TMA multicast", 9: ", CTA pairs (cta_group::2)", 10: ", CTA pairs: cta_group::2, M = 256"}.get(impl_used, "")
+        variant = {8: ", 2 x 2 CTA clusters + TMA multicast", 9: ", CTA pairs (cta_group::2)", 10: ", CTA pairs: cta_group::2, M = 256", 11: ", 2-CTA clusters sharing the A planes (TMA multicast)"}.get(impl_used, "")
         kname = "tile_kernel_i8_pair" if impl_used == 10 else "tile_kernel_i8"
         out.update(kernel=f"{kname}<{real}, {planes} int8 planes, {kernel}, {mode}> (tcgen05 kind::i8{variant})", peak=sus, frac=achieved / sus, peak_burst=burst,
                    frac_sustained=achieved / sus, frac_burst=achieved / burst, int8_tops=achieved * products, vs_float_pipe_peak=achieved / fp_pipe, float_pipe_peak_tflops=fp_pipe,

@@ -57,7 +57,7 @@ typedef struct plssvm_b200_timings {
     int impl_used;            /* 1 = SIMT FMA tiles, 2 = floating-point tensor tiles (fp64: TMA + DMMA; fp32: TMA + tcgen05 3xTF32), 3 = factorised linear,
                                * 6 / 7 = int8-slice tcgen05 tiles (fp32: 3 / 4 digit planes), 10 = int8-slice tiles on CTA pairs (the fp32 default
                                * when the A operand has at least 256 rows); experimental builds only: 4 / 5 fp32 3xTF32 variants,
-                               * 8 / 9 int8-slice variants on CTA clusters / CTA pairs (see "impl" below) */
+                               * 8 / 9 / 11 int8-slice variants on CTA clusters / CTA pairs (see "impl" below) */
     int n_devices;            /* devices (ranks) that took part in the call */
     uint64_t cg_iterations;     /* min(iter + 1, max_iter) as the reference reports it (gpu_csvm.hpp:639,646) */
     uint64_t cg_max_iterations;
@@ -94,7 +94,7 @@ const char *plssvm_b200_last_error(void);
  * 54 bits, fp32: 3 slices = 22 bits), 7 the same with 4 slices (30 bits) for fp32, 10 the kernel of 6 on CTA pairs (tcgen05.mma.cta_group::2,
  * tile_i8_pair.cuh; fp64: experimental builds only, otherwise it resolves to 6); only in builds with -DPLSSVM_B200_EXPERIMENTAL
  * (measured-but-not-faster variants kept for reference, bit-identical results): 4 / 5 fp32 3xTF32 variants (CTA pair / 128x256),
- * 8 / 9 variants of 6 (2 x 2 CTA clusters with TMA multicast / fp32 CTA pairs with cta_group::2); "max_ctas" (debugging: cap the
+ * 8 / 9 / 11 variants of 6 (2 x 2 CTA clusters with TMA multicast / fp32 CTA pairs with cta_group::2 / clusters of two CTAs that share the A planes); "max_ctas" (debugging: cap the
  * number of persistent CTAs of the tile kernels, 0 = one per SM); "check_interval" (CG iterations between host polls),
  * "verbose" (0/1: per-iteration log lines like gpu_csvm.hpp:569-571), "linear_factorized" (0/1: for the linear kernel
  * evaluate Q~ v as X (X^T v) + rank-2 terms — two streaming passes over X, O(n d) instead of O(n^2 d); default 0 = the

@@ -137,9 +137,9 @@ template <typename T>
 int i8_slices_for(const int impl) { return impl == 7 ? pb::I8<T>::S_EXACT : pb::I8<T>::S; }
 // int8-slice tile kernels: 6 default slice count, 7 exact-input slice count; experimental: 8 default slice count with 2 x 2 CTA clusters + TMA multicast,
 // 9 (fp32) CTA pairs with tcgen05.mma.cta_group::2 (tile_i8_2sm.cuh); 10: CTA pairs with the wide-N instructions (tile_i8_pair.cuh), default slice count
-inline bool is_i8(const int impl) { return impl >= 6 && impl <= 10; }
+inline bool is_i8(const int impl) { return impl >= 6 && impl <= 11; }
 // kernels whose tile range / ownership is over 256 x 256 super-tiles
-inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8 || impl == 9 || impl == 10; }
+inline bool super_tiled(const int impl) { return impl == 4 || impl == 5 || impl == 8 || impl == 9 || impl == 10 || impl == 11; }
 // rows per box of the extra B-operand copy of the digit planes (experimental CTA-pair kernel only); TILE = no extra copy
 template <typename T>
 int i8_br_b_for(const int impl) { return impl == 9 ? 64 : TILE; }
@@ -364,7 +364,7 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
                 cudaLaunchConfig_t cfg{};
                 cudaLaunchAttribute attr[1];
                 attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = 4;
+                attr[0].val.clusterDim.x = CL;
                 attr[0].val.clusterDim.y = 1;
                 attr[0].val.clusterDim.z = 1;
                 cfg.blockDim = dim3(pb::I8_THREADS);
@@ -372,12 +372,12 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
                 cfg.stream = ctx->stream;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
-                cfg.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / 4 * 4));
-                int max_clusters = 0;  // clusters of four that can be resident at once (GPC boundaries can leave a few SMs unused)
+                cfg.gridDim = dim3(static_cast<unsigned>(ctx->num_sms / CL * CL));
+                int max_clusters = 0;  // clusters that can be resident at once (GPC boundaries can leave a few SMs unused)
                 PB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-                PB_REQUIRE(max_clusters > 0, "no 4-CTA cluster of the int8-slice kernel fits on this device");
+                PB_REQUIRE(max_clusters > 0, "no CTA cluster of the int8-slice kernel fits on this device");
                 const unsigned clusters = static_cast<unsigned>(std::min<std::uint64_t>(ntiles, static_cast<std::uint64_t>(max_clusters)));
-                cfg.gridDim = dim3(4 * clusters);
+                cfg.gridDim = dim3(CL * clusters);
                 PB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
             }
         };
@@ -385,6 +385,10 @@ void launch_tiles_t(plssvm_b200_ctx *ctx, const TileParams<T> &p, const int impl
         if (EXPERIMENTAL && impl == 8) {
 #ifdef PLSSVM_B200_EXPERIMENTAL
             launch(std::integral_constant<int, pb::I8<T>::S>{}, std::integral_constant<int, 4>{});
+#endif
+        } else if (EXPERIMENTAL && impl == 11) {
+#ifdef PLSSVM_B200_EXPERIMENTAL
+            launch(std::integral_constant<int, pb::I8<T>::S>{}, std::integral_constant<int, 2>{});
 #endif
         } else if (dflt) {
             launch(std::integral_constant<int, pb::I8<T>::S>{}, std::integral_constant<int, 1>{});
@@ -453,6 +457,7 @@ int resolve_impl(const plssvm_b200_ctx *ctx, const std::size_t features = 0, con
         if (features > pb::I8_MAX_FEATURES) { return 2; }
         if (sizeof(T) == 8 && (ctx->impl == 7 || ctx->impl == 9)) { return 6; }
         if (ctx->impl == 10 && !pair_kernel_built<T>()) { return 6; }
+        if (ctx->impl == 11 && !EXPERIMENTAL) { return 6; }
         return ctx->impl;
     }
     if (ctx->impl == 4 || ctx->impl == 5) { return sizeof(T) == 4 ? ctx->impl : 2; }  // CTA-pair / wide-tile tcgen05 kernels exist for fp32 only
@@ -470,7 +475,7 @@ void launch_tiles(plssvm_b200_ctx *ctx, const TileParams<T> &p_in, const int imp
     ctx->tm.impl_used = impl;
     TileParams<T> p = p_in;
     p.slow_drain = ctx->fp32_fast_drain != 0 ? 0 : 1;
-    const bool stats = ctx->tile_stats != 0 && (impl == 6 || impl == 7 || impl == 10);
+    const bool stats = ctx->tile_stats != 0 && (impl == 6 || impl == 7 || impl == 10 || impl == 11);
     const std::size_t stat_words = static_cast<std::size_t>(ctx->num_sms) * 8;
     if (stats) {
         p.stats = workspace<unsigned long long>(ctx, plssvm_b200_ctx::WS_STATS, stat_words);
@@ -1629,12 +1634,12 @@ int plssvm_b200_set_option(plssvm_b200_ctx *ctx, const char *key, long long valu
         PB_REQUIRE(handle_live(ctx) && key != nullptr, "ctx (NULL or destroyed) or key is NULL");
         const std::string k(key);
         if (k == "impl") {
-            const bool known = value == 0 || value == 1 || value == 2 || value == 6 || value == 7 || value == 10 || (EXPERIMENTAL && (value == 4 || value == 5 || value == 8 || value == 9));
+            const bool known = value == 0 || value == 1 || value == 2 || value == 6 || value == 7 || value == 10 || (EXPERIMENTAL && (value == 4 || value == 5 || value == 8 || value == 9 || value == 11));
             PB_REQUIRE(known, std::string("impl must be 0 (auto), 1 (simt), 2 (floating-point tensor tiles), 6 (int8-slice tcgen05 tiles), 7 (int8-slice tiles with the exact-input "
                                           "slice count: fp32 4 instead of 3 slices) or 10 (int8-slice tiles on CTA pairs, cta_group::2 with the wide-N instructions)") +
                                   (EXPERIMENTAL ? "; experimental: 4 (fp32: CTA-pair 3xTF32), 5 (fp32: 128x256 3xTF32), 8 (int8-slice tiles, 2 x 2 CTA clusters with TMA multicast), 9 (fp32: "
-                                                  "int8-slice tiles on CTA pairs, cta_group::2)"
-                                                : "; 4 / 5 / 8 / 9 need a build with -DPLSSVM_B200_EXPERIMENTAL"));
+                                                  "int8-slice tiles on CTA pairs, cta_group::2), 11 (int8-slice tiles, clusters of two CTAs sharing the A planes through TMA multicast)"
+                                                : "; 4 / 5 / 8 / 9 / 11 need a build with -DPLSSVM_B200_EXPERIMENTAL"));
         } else if (k == "check_interval") {
             PB_REQUIRE(value >= 0 && value <= 1000000, "check_interval out of range");
         } else if (k == "max_ctas") {

@@ -528,11 +528,15 @@ __device__ __forceinline__ void i8_epilogue_unit(const TileParams<T> &p, T *s_ro
 // planes and the two of a cluster column the same B planes, so every CTA fetches only one half of the planes of its A block and of its B block and
 // TMA multicasts it to its mate — half the L2 -> SM traffic per CTA (the single-CTA kernel runs at 92 % of the L2 throughput cap).  A stage is
 // refilled once the MMA warps of all three CTAs that write into or read from it have released it (multicast tcgen05.commit, count 3).
+// CL = 2: a cluster of two CTAs per super-tile that share only the A planes: CTA c computes the tiles (2 I2, 2 J2 + c) and (2 I2 + 1, 2 J2 + c) one after
+// the other, each CTA fetches one half of the A planes of the current row block and multicasts it to its mate (a third less L2 -> SM traffic per CTA), the B
+// planes are fetched per CTA as on single CTAs; a stage is refilled once both MMA warps have released it (count 2).
 template <typename T, int S_, int KERNEL, int MODE, int CL, bool TS = false>
 __global__ void __launch_bounds__(I8_THREADS, 1)  // (10 warps = 3 on one SM sub-partition: 170 registers per thread at most)
 tile_kernel_i8(const TileParams<T> p) {
     using L8 = I8Layout<T, S_>;
-    static_assert(CL == 1 || CL == 4, "cluster size");
+    static_assert(CL == 1 || CL == 2 || CL == 4, "cluster size");
+    constexpr int TPW = CL == 2 ? 2 : 1;  // tiles per work item and CTA
     constexpr int S = L8::S, NH = L8::NH, UNITS = L8::UNITS, STAGES = L8::STAGES;
     extern __shared__ unsigned char smem_raw[];
     if (p.done != nullptr && *p.done != 0) { return; }
@@ -551,12 +555,13 @@ tile_kernel_i8(const TileParams<T> p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const std::uint32_t num_slabs = p.ld8 / L8::BK;
     std::uint32_t crank = 0;
-    if constexpr (CL == 4) { crank = cluster_ctarank(); }
-    const std::uint32_t cr = crank >> 1, cc = crank & 1u;  // position of this CTA inside the 2 x 2 cluster
-    const std::uint64_t work_first = (CL == 4) ? (blockIdx.x >> 2) : blockIdx.x, work_stride = (CL == 4) ? (gridDim.x >> 2) : gridDim.x;
+    if constexpr (CL != 1) { crank = cluster_ctarank(); }
+    const std::uint32_t cr = crank >> 1, cc = crank & 1u;  // CL = 4: position of this CTA inside the 2 x 2 cluster; CL = 2: cc = its tile column, cr = 0
+    const std::uint64_t work_first = blockIdx.x / CL, work_stride = gridDim.x / CL;
     const std::uint32_t S_rows = (p.T_rows + 1) >> 1, S_cols = (p.T_cols + 1) >> 1;
     // work item L -> tile (I, J) of this CTA; `valid` = false for the padding / strictly-upper tile of a super-tile (computed, never stored)
-    auto decode = [&](const std::uint64_t L, std::uint32_t &I, std::uint32_t &J) -> bool {
+    // (rr: CL = 2 only, the tile row inside the super-tile this CTA is working on)
+    auto decode = [&](const std::uint64_t L, const std::uint32_t rr, std::uint32_t &I, std::uint32_t &J) -> bool {
         if constexpr (CL == 1) {
             if constexpr (MODE == MODE_SYM) {
                 tri_decode(p.T_rows, L, I, J);
@@ -571,7 +576,7 @@ tile_kernel_i8(const TileParams<T> p) {
             } else {
                 rect_decode(S_rows, S_cols, L, I2, J2);
             }
-            I = 2 * I2 + cr;
+            I = 2 * I2 + (CL == 4 ? cr : rr);
             J = 2 * J2 + cc;
             return I < p.T_rows && J < p.T_cols && (MODE == MODE_RECT || J <= I);
         }
@@ -581,7 +586,7 @@ tile_kernel_i8(const TileParams<T> p) {
         #pragma unroll
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, CL == 4 ? 3 : 1);  // CL = 4: this CTA's MMA warp, its row mate's and its column mate's
+            mbar_init(empty0 + 8 * s, CL == 4 ? 3 : CL);  // CL = 4: this CTA's MMA warp, its row mate's and its column mate's; CL = 2: both MMA warps
         }
         mbar_init(tfull, 1);
         mbar_init(tempty, I8_EPI_THREADS / 32);  // one arrive per epilogue warp
@@ -593,7 +598,7 @@ tile_kernel_i8(const TileParams<T> p) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tcgen05_fence_before();
-    if constexpr (CL == 4) { cluster_sync_all(); }  // the mbarriers of all four CTAs exist before anyone multicasts into them
+    if constexpr (CL != 1) { cluster_sync_all(); }  // the mbarriers of all CTAs of the cluster exist before anyone multicasts into them
     __syncthreads();
     tcgen05_fence_after();
     const std::uint32_t tmem_base = *tmem_slot;
@@ -603,11 +608,12 @@ tile_kernel_i8(const TileParams<T> p) {
         if (role_entered<PB_ELECT_PRODUCER != 0>(lane)) {
             std::uint32_t stage = 0, phase = 0;
             long long w_empty = 0;  // cycles spent waiting for a free ring stage (p.stats)
-            const std::uint16_t mask_a = static_cast<std::uint16_t>(3u << (2 * cr));                // the two CTAs of this cluster row
-            const std::uint16_t mask_b = static_cast<std::uint16_t>((1u << cc) | (1u << (2 + cc)));  // the two CTAs of this cluster column
+            const std::uint16_t mask_a = static_cast<std::uint16_t>(3u << (2 * cr));                // the two CTAs of this cluster row (CL = 2: both CTAs)
+            const std::uint16_t mask_b = static_cast<std::uint16_t>((1u << cc) | (1u << (2 + cc)));  // the two CTAs of this cluster column (CL = 4)
             for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
+              for (std::uint32_t rr = 0; rr < TPW; ++rr) {
                 std::uint32_t I, J;
-                decode(L, I, J);
+                decode(L, rr, I, J);
                 // padding tiles of a super-tile (CL = 4, odd tile counts) load the last valid block instead of running past the buffers
                 const std::uint32_t Il = I < p.T_rows ? I : p.T_rows - 1, Jl = J < p.T_cols ? J : p.T_cols - 1;
                 for (int h = 0; h < UNITS; ++h) {
@@ -636,7 +642,14 @@ tile_kernel_i8(const TileParams<T> p) {
                             constexpr int S0 = (S + 1) / 2;
                             const int pa0 = cc == 0 ? 0 : S0, pa1 = cc == 0 ? S0 : S, pb0 = cr == 0 ? 0 : S0, pb1 = cr == 0 ? S0 : S;
                             bulk_load_mc(dst + pa0 * L8::A_SLICE, box_a + pa0 * L8::A_SLICE, static_cast<std::uint32_t>((pa1 - pa0) * L8::A_SLICE), bar, mask_a);
-                            if constexpr (UNITS == 1) {
+                            if constexpr (CL == 2) {  // B per CTA, as on single CTAs
+                                if constexpr (UNITS == 1) {
+                                    bulk_load(dst + L8::A_BYTES, box_b, L8::B_BYTES, bar);
+                                } else {
+                                    #pragma unroll
+                                    for (int pl = 0; pl < S; ++pl) { bulk_load(dst + L8::A_BYTES + pl * L8::B_SLICE, box_b + pl * L8::A_SLICE, L8::B_SLICE, bar); }
+                                }
+                            } else if constexpr (UNITS == 1) {
                                 bulk_load_mc(dst + L8::A_BYTES + pb0 * L8::B_SLICE, box_b + pb0 * L8::B_SLICE, static_cast<std::uint32_t>((pb1 - pb0) * L8::B_SLICE), bar, mask_b);
                             } else {
                                 for (int pl = pb0; pl < pb1; ++pl) { bulk_load_mc(dst + L8::A_BYTES + pl * L8::B_SLICE, box_b + pl * L8::A_SLICE, L8::B_SLICE, bar, mask_b); }
@@ -648,6 +661,7 @@ tile_kernel_i8(const TileParams<T> p) {
                         }
                     }
                 }
+              }
             }
             if (p.stats != nullptr) { p.stats[blockIdx.x * 8 + 3] = static_cast<unsigned long long>(w_empty); }
         }
@@ -659,9 +673,10 @@ tile_kernel_i8(const TileParams<T> p) {
             std::uint32_t kstep_parity = 0;
             long long w_full = 0, w_tempty = 0;  // cycles waiting for operands / for the epilogue to hand the accumulators back (p.stats)
             const long long c_begin = p.stats != nullptr ? clock64() : 0;
-            const std::uint16_t mask_rel = static_cast<std::uint16_t>((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));  // this CTA, its row mate, its column mate
+            const std::uint16_t mask_rel = CL == 2 ? static_cast<std::uint16_t>(3u)
+                                                   : static_cast<std::uint16_t>((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));  // this CTA, its row mate, its column mate
             for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
-                for (int h = 0; h < UNITS; ++h, ++unit_iter) {
+                for (int h = 0; h < TPW * UNITS; ++h, ++unit_iter) {  // (CL = 2: the units of both tiles of the work item)
                     const long long c0 = p.stats != nullptr ? clock64() : 0;
                     mbar_wait(tempty, (unit_iter & 1u) ^ 1u);  // epilogue has drained the accumulators of the previous unit
                     if (p.stats != nullptr) { w_tempty += clock64() - c0; }
@@ -739,20 +754,22 @@ tile_kernel_i8(const TileParams<T> p) {
         // ===== epilogue: warps 2..9; warp w owns TMEM lanes 32 (w % 4) .. + 31 and columns CPT ch .. + CPT - 1 of the unit =====
         std::uint32_t unit_iter = 0;
         for (std::uint64_t L = p.tile_lo + work_first; L < p.tile_hi; L += work_stride) {
-            std::uint32_t I, J;
-            const bool valid = decode(L, I, J);
-            const bool diag = (MODE == MODE_SYM) && (I == J);
-            const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
-            T rowacc = T(0);
-            for (int h = 0; h < UNITS; ++h, ++unit_iter) {
-                i8_epilogue_unit<T, S, KERNEL, MODE, false>(p, s_row, s_col, s_colsum, s_rowsum, tmem_base, tfull, tempty, unit_iter, I, J, h, valid, diag, qa, rowacc);
+            for (std::uint32_t rr = 0; rr < TPW; ++rr) {
+                std::uint32_t I, J;
+                const bool valid = decode(L, rr, I, J);
+                const bool diag = (MODE == MODE_SYM) && (I == J);
+                const T qa = (MODE == MODE_SYM) ? *p.QA_cost : T(0);
+                T rowacc = T(0);
+                for (int h = 0; h < UNITS; ++h, ++unit_iter) {
+                    i8_epilogue_unit<T, S, KERNEL, MODE, false>(p, s_row, s_col, s_colsum, s_rowsum, tmem_base, tfull, tempty, unit_iter, I, J, h, valid, diag, qa, rowacc);
+                }
             }
         }
     }
 
     // teardown: everyone done with TMEM before the allocating warp frees it (CL = 4: and with each other's shared memory and mbarriers)
     tcgen05_fence_before();
-    if constexpr (CL == 4) { cluster_sync_all(); }
+    if constexpr (CL != 1) { cluster_sync_all(); }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");

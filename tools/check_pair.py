@@ -18,7 +18,7 @@ import plssvm_b200 as pb  # noqa: E402
 from bench import WORKLOADS, make_device_data, matvec_flops  # noqa: E402
 from datagen import make_data  # noqa: E402
 
-A, B = 6, 10
+A, B = 6, int(([a.split("=")[1] for a in sys.argv if a.startswith("--b=")] or ["10"])[0])  # --b=11: the A-sharing 2-CTA cluster variant (experimental builds)
 be = pb.Backend(0)
 dev = torch.device("cuda", 0)
 quick = "--quick" in sys.argv
