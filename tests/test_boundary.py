@@ -32,6 +32,20 @@ def test_header_cites_reference_interfaces():
         assert cite in text
 
 
+def test_header_documents_every_option_the_library_accepts():
+    """Every key plssvm_b200_set_option accepts (backend.cu) is described in the header's comment on that entry point, and so is every value of "impl"
+    the default build accepts."""
+    src = open(os.path.join(ROOT, "plssvm_b200", "csrc", "backend.cu")).read()
+    header = open(os.path.join(ROOT, "include", "plssvm_b200.h")).read()
+    keys = sorted(set(re.findall(r'\bk [!=]= "([a-z_0-9]+)"', src)))
+    assert len(keys) >= 15 and "impl" in keys and "fp32_pair" in keys
+    for k in keys:
+        assert f'"{k}"' in header, f'option "{k}" is accepted by plssvm_b200_set_option but not documented in include/plssvm_b200.h'
+    known = re.search(r"const bool known = ([^;]+);", src).group(1).split("(EXPERIMENTAL")[0]
+    for v in re.findall(r"value == (\d+)", known):
+        assert re.search(rf"\b{v}\b", header[header.index("tuning / debugging knobs"):]), f"impl = {v} not documented"
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
